@@ -1,0 +1,179 @@
+/* cokrig.h -- C ABI of libcokrig_b200.so: the B200 (sm_100a) cokriging hot path.
+ *
+ * The reference (91Mrwu/sif-xco2-cokriging) is pure Python and has no FFI of its own; its hot path
+ * is the set of numpy/scipy/sklearn/pandas calls cited below (paths relative to the reference root).
+ * Each entry point here replaces one of those call groups; the drop-in Python modules under
+ * sif-xco2-cokriging_b200/src bind them with ctypes (see INTEGRATION.md for the binding stubs).
+ *
+ * Conventions
+ *   - plain C types only: pointers, sizes, scalars.  No torch / C++ types cross this boundary.
+ *   - every `const double*` / `double*` named *_dev (and all matrix/vector arguments unless marked
+ *     HOST) is a DEVICE pointer on the current CUDA device; `params` vectors are HOST pointers.
+ *   - matrices are FP64, row-major, with an explicit leading dimension `ld` (elements per row).
+ *   - coordinates are (n x 2) row-major FP64: [lat, lon] in degrees for CK_METRIC_HAVERSINE,
+ *     [x, y] for CK_METRIC_EUCLID (src/fields.py:318-342).
+ *   - `params` is the reference's flat parameter vector, MaternParams.get_values() order
+ *     (src/model.py:130-152): n_procs=2: sigma11,sigma22, nu11,nu12,nu22, len11,len12,len22,
+ *     nugget11,nugget22, rho12 (11 values); n_procs=1: sigma, nu, len_scale, nugget (4 values).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All work is
+ *     enqueued asynchronously on it; nothing synchronises unless stated.
+ *   - return value: CK_OK (0), or a negative CK_ERR_* code; ck_last_error() gives the text.
+ *     Numerical failures (non-positive pivot) are reported through the `info` outputs, LAPACK
+ *     style, never through the return value.
+ *   - no hidden device allocations: scratch comes from the caller via *_workspace_bytes().
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns CK_ERR_CUDA.
+ */
+#ifndef COKRIG_H
+#define COKRIG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int64_t ck_i64;
+
+#define CK_OK 0
+#define CK_ERR_ARG (-1)         /* invalid argument (null pointer, negative size, bad enum, ld too small) */
+#define CK_ERR_CUDA (-2)        /* CUDA runtime error (launch failure, no device, ...) */
+#define CK_ERR_UNSUPPORTED (-3) /* valid request outside what the kernels implement (e.g. n_procs > 2) */
+
+#define CK_METRIC_EUCLID 0    /* scipy.spatial.distance.cdist(X1, X2)              src/fields.py:342 */
+#define CK_METRIC_HAVERSINE 1 /* sklearn haversine_distances(radians(X)) * 6371     src/fields.py:334-336 */
+
+int ck_version(void);
+const char* ck_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1  Matern (cross-)covariance assembly
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Elementwise covariance of a distance array: out[k] = scale * rho(h[k] | nu, len_scale)
+ * (+ nugget where h[k] == 0).  Replaces model._matern_correlation + the scaling in
+ * MultivariateMatern.correlation/covariance/cross_covariance  (src/model.py:188-207, 354-385).
+ * scale = sigma_i^2 (covariance) or rho_ij * prod(sigma) (cross_covariance); pass nugget = 0 for
+ * cross blocks or use_nugget=False; scale = 1, nugget = 0 gives the bare correlation. */
+int ck_matern_eval(const double* h_dev, ck_i64 n, double scale, double nu, double len_scale, double nugget,
+                   double* out_dev, void* stream);
+
+/* Pairwise distances only: out[i*ld + j] = d(xy1[i], xy2[j]).
+ * Replaces fields.distance_matrix(X1, X2, units, fast_dist)  (src/fields.py:318-342). */
+int ck_distance_block(const double* xy1_dev, ck_i64 n1, const double* xy2_dev, ck_i64 n2, int metric,
+                      double* out_dev, ck_i64 ld, void* stream);
+
+/* Fused coordinates -> distance -> Matern -> scale/nugget for one block:
+ *   out[i*ld + j] = scale * rho(d(xy1[i], xy2[j])) (+ nugget where d == 0).
+ * If out_t != NULL the transposed block is written as well: out_t[j*ld_t + i] = out[i*ld + j].
+ * symmetric != 0 requires xy1 == xy2 (same points): only tiles on/above the diagonal are evaluated
+ * and mirrored into the lower triangle of `out` (out_t is ignored).
+ * Replaces distance_matrix + MultivariateMatern.covariance/cross_covariance on one block
+ * (src/joint_prediction.py:94-122, src/point_prediction.py:98-113, src/sim.py:45-50). */
+int ck_matern_block(const double* xy1_dev, ck_i64 n1, const double* xy2_dev, ck_i64 n2, int metric, double scale,
+                    double nu, double len_scale, double nugget, double* out_dev, ck_i64 ld, double* out_t_dev,
+                    ck_i64 ld_t, int symmetric, void* stream);
+
+/* Joint covariance of the stacked data vector, block order [[C00, C01], [C01^T, C11]]
+ * (n_procs = 2, N = n0 + n1) or the single block C00 (n_procs = 1, N = n0; xy_b ignored).
+ * Replaces joint_prediction.Predictor._joint_cov (src/joint_prediction.py:124-153),
+ * point_prediction.Predictor._cov_blocks (src/point_prediction.py:98-113) and
+ * sim.BivariateRandomField._joint_cov_matrix (src/sim.py:45-50). */
+int ck_joint_cov(const double* xy0_dev, ck_i64 n0, const double* xy1_dev, ck_i64 n1, const double* params /*HOST*/,
+                 int n_procs, int metric, double* sigma_dev, ck_i64 ld, void* stream);
+
+/* Covariances between m prediction targets of process i_pred and the stacked data, TARGET-MAJOR:
+ *   cpd[c*ld + k] = Cov(Y_i(target c), Z(stacked datum k)),  k over process 0 then process 1
+ * (own-process columns use covariance(use_nugget=True), the others cross_covariance).
+ * This is the transpose of joint_prediction.Predictor._pred_cross_cov (src/joint_prediction.py:104-122). */
+int ck_cross_cov(const double* xy0_dev, ck_i64 n0, const double* xy1_dev, ck_i64 n1, const double* xyp_dev, ck_i64 m,
+                 const double* params /*HOST*/, int n_procs, int i_pred, int metric, double* cpd_dev, ck_i64 ld,
+                 void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K3  dense FP64 Cholesky, triangular solve, simple-cokriging prediction
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Scratch needed by ck_potrf for an n x n matrix (inverses of the 128 x 128 diagonal blocks of L,
+ * kept for the blocked triangular solves). */
+size_t ck_potrf_workspace_bytes(ck_i64 n);
+
+/* In-place lower Cholesky A = L L^T (row-major; the strict upper triangle is not referenced and is
+ * left untouched).  *info_dev (device int) = 0 on success, k > 0 if the leading minor of order k is
+ * not positive definite (LAPACK dpotrf convention; the factor is then invalid).
+ * Replaces scipy.linalg.cho_factor(lower=True) / cholesky(lower=True)
+ * (src/joint_prediction.py:68-69, src/point_prediction.py:209-210, src/sim.py:42). */
+int ck_potrf(double* a_dev, ck_i64 n, ck_i64 ld, void* ws_dev, int* info_dev, void* stream);
+
+/* Forward substitution with many right-hand sides stored TARGET-MAJOR: on entry rhs is (nrhs x n),
+ * row c holding one right-hand side; on exit row c holds L^{-1} rhs_c.  Needs the ws of ck_potrf. */
+int ck_trsm_lower(const double* l_dev, ck_i64 n, ck_i64 ld, const void* ws_dev, double* rhs_dev, ck_i64 nrhs,
+                  ck_i64 ld_rhs, void* stream);
+
+/* Simple cokriging from the factor: cpd is ((m+1) x n) as produced by ck_cross_cov with one spare
+ * row; z (n) is the stacked data vector.  On exit rows 0..m-1 of cpd hold V = L^{-1} c and row m
+ * holds y = L^{-1} z;  pred[c] = V_c . y  (= c^T Sigma^{-1} z),  var[c] = c0 - |V_c|^2
+ * (= c0 - c^T Sigma^{-1} c, may be slightly negative; the caller applies nan_to_num(sqrt())).
+ * Replaces cho_solve + the two matmuls + diagonal of src/joint_prediction.py:68-78. */
+int ck_potrs_predict(const double* l_dev, ck_i64 n, ck_i64 ld, const void* ws_dev, double* cpd_dev, ck_i64 m,
+                     ck_i64 ld_c, const double* z_dev, double c0, double* pred_dev, double* var_dev, void* stream);
+
+/* logdet(A) = 2 sum_k log L_kk from the factor -> *out_dev (device double). */
+int ck_logdet(const double* l_dev, ck_i64 n, ck_i64 ld, double* out_dev, void* stream);
+
+/* Gaussian negative log-likelihood 0.5 (z^T Sigma^-1 z + logdet Sigma + N log 2pi) of the stacked
+ * data under the model: assembles Sigma into sigma_dev (N x N, ld), factors it in place, solves.
+ * scratch_dev: at least N doubles.  out_dev[0] = nll, out_dev[1] = quadratic form, out_dev[2] = logdet.
+ * No counterpart in the current reference src/ (the likelihood fit of the north star). */
+int ck_nll(const double* xy0_dev, ck_i64 n0, const double* xy1_dev, ck_i64 n1, const double* params /*HOST*/,
+           int n_procs, int metric, const double* z_dev, double* sigma_dev, ck_i64 ld, void* ws_dev,
+           double* scratch_dev, double* out_dev, int* info_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K2  empirical (cross-)semivariogram pair binning
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Pass 1: over all pairs (a < b if same_field, else all a, b) with d <= max_dist:
+ *   out_dev[0] = min{d : d > 0} (+inf if none), out_dev[1] = max d (-inf if none),
+ *   out_dev[2] = number of retained pairs (as double, exact below 2^53).
+ * Replaces the two reductions of fields._construct_variogram_bins (src/fields.py:394-395). */
+int ck_vario_minmax(const double* xya_dev, ck_i64 na, const double* xyb_dev, ck_i64 nb, int metric, int same_field,
+                    double max_dist, double* out_dev, void* stream);
+
+size_t ck_vario_bin_workspace_bytes(ck_i64 na, ck_i64 nb, int n_bins);
+
+/* Pass 2: bin every retained pair with pandas.cut(include_lowest=True) semantics on `edges`
+ * (n_bins + 1 ascending edges, HOST): bin k <=> edges[k] < d <= edges[k+1], d == edges[0] -> bin 0,
+ * d > edges[n_bins] dropped.  Cloud value 0.5 (ra - rb)^2 (covariogram == 0) or ra * rb, with
+ * ra = va - mean_a, rb = vb - mean_b (src/fields.py:378-386).  counts_dev: n_bins uint64 (bit-exact);
+ * sums_dev: n_bins FP64 sums accumulated in a fixed, launch-geometry-independent order.
+ * Replaces _variogram_cloud + pd.cut + groupby.agg  (src/fields.py:192-222). */
+int ck_vario_bin(const double* xya_dev, const double* va_dev, ck_i64 na, double mean_a, const double* xyb_dev,
+                 const double* vb_dev, ck_i64 nb, double mean_b, int metric, int same_field, int covariogram,
+                 double max_dist, const double* edges /*HOST*/, int n_bins, unsigned long long* counts_dev,
+                 double* sums_dev, void* ws_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K4  batched local-neighbourhood cokriging (point prediction)
+ * ---------------------------------------------------------------------------------------------- */
+
+size_t ck_local_predict_workspace_bytes(ck_i64 m, ck_i64 kmax);
+
+/* Pass 1: k_dev[c] = number of data (both processes) within max_dist of target c
+ * (cv != 0: data of process i_pred at distance exactly 0 are excluded, src/point_prediction.py:140-142). */
+int ck_local_count(const double* xy0_dev, ck_i64 n0, const double* xy1_dev, ck_i64 n1, const double* xyp_dev, ck_i64 m,
+                   int n_procs, int i_pred, int metric, double max_dist, int cv, int* k_dev, void* stream);
+
+/* Pass 2: for every target: gather neighbours (process 0 then 1, index order), assemble the local
+ * covariance from coordinates, factor, solve.  pred/sd follow src/point_prediction.py:200-241:
+ * NaN when there is no neighbour or the local matrix is not positive definite (info_dev[c] > 0);
+ * sd = sqrt(max(c0 - w.c, 0)) with NaN -> 0.  kmax = max_c k_dev[c] (from pass 1). */
+int ck_local_predict(const double* xy0_dev, const double* z0_dev, ck_i64 n0, const double* xy1_dev, const double* z1_dev,
+                     ck_i64 n1, const double* xyp_dev, ck_i64 m, const double* params /*HOST*/, int n_procs, int i_pred,
+                     int metric, double max_dist, int cv, const int* k_dev, ck_i64 kmax, double* pred_dev,
+                     double* sd_dev, int* info_dev, void* ws_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COKRIG_H */

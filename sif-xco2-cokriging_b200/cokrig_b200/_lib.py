@@ -1,0 +1,83 @@
+"""ctypes binding of libcokrig_b200.so (the C ABI declared in include/cokrig.h).
+
+There is no CPU fallback: if the shared library is missing or cannot be loaded this module raises,
+and every compute wrapper in ``cokrig_b200.ops`` raises when no CUDA device is present.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_int, c_int64, c_size_t, c_ulonglong, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get("COKRIG_B200_LIB", os.path.join(_HERE, "libcokrig_b200.so"))
+
+CK_OK = 0
+CK_ERR_ARG = -1
+CK_ERR_CUDA = -2
+CK_ERR_UNSUPPORTED = -3
+METRIC_EUCLID = 0
+METRIC_HAVERSINE = 1
+
+
+class CokrigError(RuntimeError):
+    """A C-ABI call returned a CK_ERR_* status."""
+
+
+def _load() -> ctypes.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python sif-xco2-cokriging_b200/build.py` "
+            "(or __graft_entry__.build()). cokrig_b200 has no CPU fallback.")
+    return ctypes.CDLL(LIB_PATH)
+
+
+lib = _load()
+
+_dp = c_void_p  # device pointers are passed as integers (torch.Tensor.data_ptr())
+_hp = POINTER(c_double)  # host double arrays
+
+# name -> (restype, argtypes); mirrors include/cokrig.h one to one
+SIGNATURES = {
+    "ck_version": (c_int, []),
+    "ck_last_error": (c_char_p, []),
+    "ck_matern_eval": (c_int, [_dp, c_int64, c_double, c_double, c_double, c_double, _dp, c_void_p]),
+    "ck_distance_block": (c_int, [_dp, c_int64, _dp, c_int64, c_int, _dp, c_int64, c_void_p]),
+    "ck_matern_block": (c_int, [_dp, c_int64, _dp, c_int64, c_int, c_double, c_double, c_double, c_double,
+                                _dp, c_int64, _dp, c_int64, c_int, c_void_p]),
+    "ck_joint_cov": (c_int, [_dp, c_int64, _dp, c_int64, _hp, c_int, c_int, _dp, c_int64, c_void_p]),
+    "ck_cross_cov": (c_int, [_dp, c_int64, _dp, c_int64, _dp, c_int64, _hp, c_int, c_int, c_int, _dp, c_int64,
+                             c_void_p]),
+    "ck_potrf_workspace_bytes": (c_size_t, [c_int64]),
+    "ck_potrf": (c_int, [_dp, c_int64, c_int64, _dp, _dp, c_void_p]),
+    "ck_trsm_lower": (c_int, [_dp, c_int64, c_int64, _dp, _dp, c_int64, c_int64, c_void_p]),
+    "ck_potrs_predict": (c_int, [_dp, c_int64, c_int64, _dp, _dp, c_int64, c_int64, _dp, c_double, _dp, _dp,
+                                 c_void_p]),
+    "ck_logdet": (c_int, [_dp, c_int64, c_int64, _dp, c_void_p]),
+    "ck_nll": (c_int, [_dp, c_int64, _dp, c_int64, _hp, c_int, c_int, _dp, _dp, c_int64, _dp, _dp, _dp, _dp,
+                       c_void_p]),
+    "ck_vario_minmax": (c_int, [_dp, c_int64, _dp, c_int64, c_int, c_int, c_double, _dp, c_void_p]),
+    "ck_vario_bin_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int]),
+    "ck_vario_bin": (c_int, [_dp, _dp, c_int64, c_double, _dp, _dp, c_int64, c_double, c_int, c_int, c_int,
+                             c_double, _hp, c_int, _dp, _dp, _dp, c_void_p]),
+    "ck_local_predict_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "ck_local_count": (c_int, [_dp, c_int64, _dp, c_int64, _dp, c_int64, c_int, c_int, c_int, c_double, c_int,
+                               _dp, c_void_p]),
+    "ck_local_predict": (c_int, [_dp, _dp, c_int64, _dp, _dp, c_int64, _dp, c_int64, _hp, c_int, c_int, c_int,
+                                 c_double, c_int, _dp, c_int64, _dp, _dp, _dp, _dp, c_void_p]),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)  # AttributeError here = library/header mismatch: fail loudly
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def last_error() -> str:
+    msg = lib.ck_last_error()
+    return msg.decode() if msg else ""
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != CK_OK:
+        raise CokrigError(f"{what or 'cokrig_b200'} failed (status {rc}): {last_error()}")

@@ -1,0 +1,521 @@
+// ck_chol.cu -- K3: blocked FP64 Cholesky, blocked triangular solves and the simple-cokriging
+// prediction epilogue for sm_100a.
+//
+// Structure (right-looking, panel width CK_NB = 128, matrix row-major, lower triangle):
+//   for each diagonal block k:
+//     ck_potf2_inv_kernel   one CTA, register-resident 128x128 elimination: L_kk in place and
+//                           X_k = L_kk^{-1} into the workspace (kept for the solves)
+//     ck_gemm_nt_kernel     panel  A[k+1:, k] <- A[k+1:, k] X_k^T                (TRSM as GEMM, in place)
+//     ck_gemm_nt_kernel     trailing A[k+1:, k+1:] -= P P^T on lower tiles only (DSYRK)
+// All O(N^3) work is in ck_gemm_nt_kernel: C (-)= A B^T with both operands K-contiguous, computed by
+// FP64 tensor-core DMMA (mma.sync m8n8k4 f64 -- tcgen05 has no f64 kind), operands staged through a
+// 3-stage cp.async shared-memory pipeline with a conflict-free padded layout, accumulators in
+// registers (initialised from C so the update needs no separate epilogue read).
+// The triangular solve with many right-hand sides keeps the RHS TARGET-MAJOR (one right-hand side
+// per row) so that it is the same NT GEMM:  V[:, k] = R[:, k] X_k^T ;  R[:, k+1:] -= V[:, k] L[k+1:, k]^T.
+#include "ck_common.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// DMMA GEMM   C = A B^T  (mode 0)   or   C = C - A B^T  (mode 1)
+// ------------------------------------------------------------------------------------------------
+constexpr int G_BK = 16;            // k-depth per pipeline stage
+constexpr int G_LDS = G_BK + 4;     // padded smem row stride (doubles): stride % 16 == 4 -> conflict-free fragments
+constexpr int G_STAGES = 3;
+constexpr int G_THREADS = 256;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem, int src_bytes) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+struct GemmArgs {
+  const double* A; long long lda;  // M x K
+  const double* B; long long ldb;  // N x K
+  double* C; long long ldc;        // M x N
+  long long M, N, K;
+  int mode;        // 0: C = A B^T, 1: C = C - A B^T
+  int lower_only;  // 1: C square, only tiles intersecting the lower triangle; entries with col > row not stored
+};
+
+// CTA tile (32*WM) x (32*WN); each of the 8 warps owns a 32 x 32 sub-tile = 4 x 4 DMMA tiles.
+template <int WM, int WN, bool VEC16>
+__global__ void __launch_bounds__(G_THREADS, 2) ck_gemm_nt_kernel(GemmArgs g) {
+  constexpr int BM = 32 * WM, BN = 32 * WN;
+  constexpr int STAGE_ELEMS = (BM + BN) * G_LDS;
+  extern __shared__ __align__(16) double smem[];
+  long long tm, tn;
+  if (g.lower_only) {
+    // linear tile id -> (row tile tm, col tile tn) over the lower block-triangle; row tm has RB*(tm+1) tiles
+    constexpr int RB = (BM >= BN) ? BM / BN : 1;
+    const long long t = blockIdx.x;
+    long long r = (long long)((sqrt(8.0 * (double)t / RB + 1.0) - 1.0) * 0.5);
+    while (RB * (r + 1) * (r + 2) / 2 <= t) ++r;
+    while (RB * r * (r + 1) / 2 > t) --r;
+    tm = r;
+    tn = t - RB * r * (r + 1) / 2;
+  } else {
+    tm = blockIdx.y;
+    tn = blockIdx.x;
+  }
+  const long long m0 = tm * BM, n0 = tn * BN;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp / WN, wn = warp % WN;
+  const int g4 = lane >> 2, t4 = lane & 3;
+
+  auto load_stage = [&](int stage, long long k0) {
+    double* base = smem + stage * STAGE_ELEMS;
+    if (VEC16) {
+      constexpr int CH = G_BK / 2;  // 16-byte chunks per row
+#pragma unroll
+      for (int idx = tid; idx < (BM + BN) * CH; idx += G_THREADS) {
+        const int row = idx / CH, ch = idx % CH;
+        const long long gk = k0 + ch * 2;
+        const bool isA = row < BM;
+        const long long gr = isA ? m0 + row : n0 + (row - BM);
+        const long long lim = isA ? g.M : g.N;
+        long long rem = (g.K - gk) * 8;
+        int bytes = (gr < lim && rem > 0) ? (rem >= 16 ? 16 : (int)rem) : 0;
+        const double* src = (isA ? g.A + (bytes ? gr * g.lda : 0) : g.B + (bytes ? gr * g.ldb : 0)) + (bytes ? gk : 0);
+        cp_async16(base + row * G_LDS + ch * 2, src, bytes);
+      }
+    } else {
+#pragma unroll
+      for (int idx = tid; idx < (BM + BN) * G_BK; idx += G_THREADS) {
+        const int row = idx / G_BK, ch = idx % G_BK;
+        const long long gk = k0 + ch;
+        const bool isA = row < BM;
+        const long long gr = isA ? m0 + row : n0 + (row - BM);
+        const long long lim = isA ? g.M : g.N;
+        const int bytes = (gr < lim && gk < g.K) ? 8 : 0;
+        const double* src = (isA ? g.A + (bytes ? gr * g.lda : 0) : g.B + (bytes ? gr * g.ldb : 0)) + (bytes ? gk : 0);
+        cp_async8(base + row * G_LDS + ch, src, bytes);
+      }
+    }
+  };
+
+  const long long KT = (g.K + G_BK - 1) / G_BK;
+#pragma unroll
+  for (int s = 0; s < G_STAGES - 1; ++s) {
+    if (s < KT) load_stage(s, (long long)s * G_BK);
+    cp_async_commit();
+  }
+
+  // accumulators: acc[mi][ni][0..1] = C[m0 + wm*32 + mi*8 + g4][n0 + wn*32 + ni*8 + 2*t4 + {0,1}]
+  double acc[4][4][2];
+  const long long crow0 = m0 + wm * 32 + g4, ccol0 = n0 + wn * 32 + 2 * t4;
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) {
+      acc[mi][ni][0] = 0.0;
+      acc[mi][ni][1] = 0.0;
+      if (g.mode == 1) {
+        const long long r = crow0 + mi * 8, c = ccol0 + ni * 8;
+        if (r < g.M) {
+          const double* p = g.C + r * g.ldc + c;
+          if (VEC16 && c + 1 < g.N) {
+            const double2 v = *reinterpret_cast<const double2*>(p);
+            acc[mi][ni][0] = v.x;
+            acc[mi][ni][1] = v.y;
+          } else {
+            if (c < g.N) acc[mi][ni][0] = p[0];
+            if (c + 1 < g.N) acc[mi][ni][1] = p[1];
+          }
+        }
+      }
+    }
+  const unsigned long long sign = (g.mode == 1) ? 0x8000000000000000ULL : 0ULL;
+
+  for (long long kt = 0; kt < KT; ++kt) {
+    cp_async_wait<G_STAGES - 2>();
+    __syncthreads();
+    {
+      const long long nk = kt + G_STAGES - 1;
+      if (nk < KT) load_stage((int)(nk % G_STAGES), nk * G_BK);
+      cp_async_commit();
+    }
+    const double* As = smem + (int)(kt % G_STAGES) * STAGE_ELEMS + (wm * 32 + g4) * G_LDS + t4;
+    const double* Bs = smem + (int)(kt % G_STAGES) * STAGE_ELEMS + (BM + wn * 32 + g4) * G_LDS + t4;
+#pragma unroll
+    for (int kk = 0; kk < G_BK; kk += 4) {
+      double a[4], b[4];
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+        a[mi] = __longlong_as_double(__double_as_longlong(As[mi * 8 * G_LDS + kk]) ^ sign);
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) b[ni] = Bs[ni * 8 * G_LDS + kk];
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();  // all operand reads of this CTA are complete before any store (in-place TRSM safety)
+
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) {
+      const long long r = crow0 + mi * 8, c = ccol0 + ni * 8;
+      if (r >= g.M) continue;
+      double* p = g.C + r * g.ldc + c;
+      const bool ok0 = c < g.N && (!g.lower_only || c <= r);
+      const bool ok1 = c + 1 < g.N && (!g.lower_only || c + 1 <= r);
+      if (VEC16 && ok0 && ok1) {
+        *reinterpret_cast<double2*>(p) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+      } else {
+        if (ok0) p[0] = acc[mi][ni][0];
+        if (ok1) p[1] = acc[mi][ni][1];
+      }
+    }
+}
+
+template <int WM, int WN>
+static int gemm_launch(const GemmArgs& g, cudaStream_t st) {
+  constexpr int BM = 32 * WM, BN = 32 * WN;
+  constexpr size_t SMEM = (size_t)G_STAGES * (BM + BN) * G_LDS * sizeof(double);
+  if (g.M <= 0 || g.N <= 0) return CK_OK;
+  const bool vec = ((((uintptr_t)g.A | (uintptr_t)g.B | (uintptr_t)g.C) & 15) == 0) && !((g.lda | g.ldb | g.ldc) & 1);
+  static bool attr_done = false;
+  if (!attr_done) {
+    CK_CUDA(cudaFuncSetAttribute(ck_gemm_nt_kernel<WM, WN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    CK_CUDA(cudaFuncSetAttribute(ck_gemm_nt_kernel<WM, WN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    attr_done = true;
+  }
+  const long long tm = (g.M + BM - 1) / BM, tn = (g.N + BN - 1) / BN;
+  dim3 grid;
+  if (g.lower_only) {
+    constexpr int RB = (BM >= BN) ? BM / BN : 1;
+    CK_REQUIRE(BM >= BN, "lower_only needs BM >= BN");
+    long long tiles = RB * tm * (tm + 1) / 2;
+    // the last row tile may extend past N in columns: tiles with n0 >= N are launched but exit at the store guards
+    grid = dim3((unsigned)tiles, 1, 1);
+  } else {
+    CK_REQUIRE(tm <= 65535, "too many row tiles");
+    grid = dim3((unsigned)tn, (unsigned)tm, 1);
+  }
+  if (vec) ck_gemm_nt_kernel<WM, WN, true><<<grid, G_THREADS, SMEM, st>>>(g);
+  else ck_gemm_nt_kernel<WM, WN, false><<<grid, G_THREADS, SMEM, st>>>(g);
+  CK_LAUNCH_CHECK();
+  return CK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Diagonal block: Cholesky + inverse of the factor, one CTA of 1024 threads, elements in registers.
+// Thread (tx, ty) owns A[ty + 32a][tx + 32b], a, b in 0..3 (2-D cyclic -> balanced as columns retire).
+// Phase 1 (LDL^T-style elimination, one barrier per column): publish column j, every thread applies
+//   A[i][k] -= A[i][j] A[k][j] / d_j to its lower-triangle elements; L[i][j] = A[i][j] / sqrt(d_j).
+// Phase 2 (forward substitution on the identity, one barrier per row): X = L^{-1}.
+// Rows/cols >= nb are padded with the identity so partial blocks need no special cases.
+// ------------------------------------------------------------------------------------------------
+constexpr int P_SMEM_DOUBLES = CK_NB * CK_NB + 2 * (CK_NB + 8) + 2 * CK_NB;
+
+__global__ void __launch_bounds__(1024, 1)
+    ck_potf2_inv_kernel(double* __restrict__ A, long long ld, int nb, double* __restrict__ X, int* info, int k0) {
+  extern __shared__ __align__(16) double sm[];
+  double* Lsh = sm;                           // Lsh[j*128 + i] = L[i][j]
+  double* colbuf = Lsh + CK_NB * CK_NB;       // 2 x (128 + 8): published column/row; [128]=1/d, [129]=sqrt d, [130]=1/sqrt d
+  double* rsh = colbuf + 2 * (CK_NB + 8);     // 1/sqrt(d_j) = 1/L[j][j]
+  double* sqh = rsh + CK_NB;                  // sqrt(d_j)
+  __shared__ int bad;
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  if (tid == 0) bad = 0;
+  double a[4][4];
+#pragma unroll
+  for (int ai = 0; ai < 4; ++ai)
+#pragma unroll
+    for (int bi = 0; bi < 4; ++bi) {
+      const int i = ty + 32 * ai, k = tx + 32 * bi;
+      double v = (i == k) ? 1.0 : 0.0;
+      if (i < nb && k < nb) v = (k <= i) ? A[(long long)i * ld + k] : 0.0;
+      a[ai][bi] = v;
+    }
+  __syncthreads();
+#pragma unroll
+  for (int bj = 0; bj < 4; ++bj) {
+    for (int tj = 0; tj < 32; ++tj) {
+      const int j = bj * 32 + tj;
+      double* col = colbuf + (j & 1) * (CK_NB + 8);
+      if (tx == tj) {
+#pragma unroll
+        for (int ai = bj; ai < 4; ++ai) col[ty + 32 * ai] = a[ai][bj];
+        if (ty == tj) {  // owner of the pivot
+          const double d = a[bj][bj];
+          const double sq = sqrt(d);
+          col[CK_NB] = 1.0 / d;
+          col[CK_NB + 1] = sq;
+          col[CK_NB + 2] = 1.0 / sq;
+          if (!(d > 0.0) && bad == 0) bad = j + 1;
+        }
+      }
+      __syncthreads();
+      const double invd = col[CK_NB];
+      if (tid < CK_NB) {
+        const double rs = col[CK_NB + 2];
+        Lsh[j * CK_NB + tid] = (tid > j) ? col[tid] * rs : (tid == j ? col[CK_NB + 1] : 0.0);
+        if (tid == 0) {
+          rsh[j] = rs;
+          sqh[j] = col[CK_NB + 1];
+        }
+      }
+#pragma unroll
+      for (int ai = bj; ai < 4; ++ai) {
+        const int i = ty + 32 * ai;
+        if (i > j) {
+          const double li = col[i] * invd;
+#pragma unroll
+          for (int bi = bj; bi <= ai; ++bi) {
+            const int k = tx + 32 * bi;
+            if (k > j && k <= i) a[ai][bi] -= li * col[k];
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // L to global: L[i][k] = a * rs_k (k < i), sqrt(d_k) on the diagonal -- same bits as Lsh
+#pragma unroll
+  for (int ai = 0; ai < 4; ++ai)
+#pragma unroll
+    for (int bi = 0; bi < 4; ++bi) {
+      const int i = ty + 32 * ai, k = tx + 32 * bi;
+      if (i < nb && k <= i) A[(long long)i * ld + k] = (k == i) ? sqh[k] : a[ai][bi] * rsh[k];
+    }
+  // phase 2: X = L^{-1}
+  double b[4][4];
+#pragma unroll
+  for (int ai = 0; ai < 4; ++ai)
+#pragma unroll
+    for (int bi = 0; bi < 4; ++bi) b[ai][bi] = (ty + 32 * ai == tx + 32 * bi) ? 1.0 : 0.0;
+#pragma unroll
+  for (int bj = 0; bj < 4; ++bj) {
+    for (int tj = 0; tj < 32; ++tj) {
+      const int j = bj * 32 + tj;
+      double* row = colbuf + (j & 1) * (CK_NB + 8);
+      if (ty == tj) {
+        const double rs = rsh[j];
+#pragma unroll
+        for (int bi = 0; bi <= bj; ++bi) {
+          const double xv = b[bj][bi] * rs;
+          b[bj][bi] = xv;
+          row[tx + 32 * bi] = xv;
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int ai = bj; ai < 4; ++ai) {
+        const int i = ty + 32 * ai;
+        if (i > j) {
+          const double lij = Lsh[j * CK_NB + i];
+#pragma unroll
+          for (int bi = 0; bi <= bj; ++bi) b[ai][bi] -= lij * row[tx + 32 * bi];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int ai = 0; ai < 4; ++ai)
+#pragma unroll
+    for (int bi = 0; bi < 4; ++bi) {
+      const int i = ty + 32 * ai, c = tx + 32 * bi;
+      X[i * CK_NB + c] = (c <= i) ? b[ai][bi] : 0.0;
+    }
+  if (tid == 0 && bad != 0 && *info == 0) *info = k0 + bad;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small reductions (fixed summation order: strided per-thread partials, then a shared-memory tree)
+// ------------------------------------------------------------------------------------------------
+template <int T>
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  red[threadIdx.x] = v;
+  __syncthreads();
+#pragma unroll
+  for (int s = T / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  const double r = red[0];
+  __syncthreads();
+  return r;
+}
+
+// one CTA per target row c:  pred[c] = V_c . y ;  var[c] = c0 - |V_c|^2
+__global__ void __launch_bounds__(256) ck_predict_rows_kernel(const double* __restrict__ V, long long ldv, long long n,
+                                                              const double* __restrict__ y, double c0,
+                                                              double* __restrict__ pred, double* __restrict__ var) {
+  __shared__ double red[256];
+  const long long c = blockIdx.x;
+  const double* v = V + c * ldv;
+  double s2 = 0.0, sy = 0.0;
+  for (long long k = threadIdx.x; k < n; k += 256) {
+    const double x = v[k];
+    s2 += x * x;
+    sy += x * y[k];
+  }
+  s2 = block_sum<256>(s2, red);
+  sy = block_sum<256>(sy, red);
+  if (threadIdx.x == 0) {
+    pred[c] = sy;
+    var[c] = c0 - s2;
+  }
+}
+
+// out[0] = 2 sum log L_kk   (what = 0)      out[0] = sum y_k^2   (what = 1, `ld` ignored)
+__global__ void __launch_bounds__(1024) ck_diag_reduce_kernel(const double* __restrict__ L, long long ld, long long n,
+                                                              int what, double* __restrict__ out) {
+  __shared__ double red[1024];
+  double s = 0.0;
+  for (long long k = threadIdx.x; k < n; k += 1024) {
+    if (what == 0) s += log(L[k * ld + k]);
+    else { const double x = L[k]; s += x * x; }
+  }
+  s = block_sum<1024>(s, red);
+  if (threadIdx.x == 0) out[0] = (what == 0) ? 2.0 * s : s;
+}
+
+__global__ void ck_nll_combine_kernel(double* out, long long n) {
+  // out[1] = quadratic form, out[2] = logdet  ->  out[0] = 0.5 (quad + logdet + n log 2pi)
+  out[0] = 0.5 * (out[1] + out[2] + (double)n * 1.8378770664093453);
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" size_t ck_potrf_workspace_bytes(ck_i64 n) {
+  if (n <= 0) return 0;
+  const size_t nblk = (size_t)((n + CK_NB - 1) / CK_NB);
+  return nblk * CK_NB * CK_NB * sizeof(double);
+}
+
+static int potf2_launch(double* a, long long ld, int nb, double* x, int* info, int k0, cudaStream_t st) {
+  constexpr size_t SMEM = P_SMEM_DOUBLES * sizeof(double);
+  static bool attr_done = false;
+  if (!attr_done) {
+    CK_CUDA(cudaFuncSetAttribute(ck_potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    attr_done = true;
+  }
+  ck_potf2_inv_kernel<<<1, 1024, SMEM, st>>>(a, ld, nb, x, info, k0);
+  CK_LAUNCH_CHECK();
+  return CK_OK;
+}
+
+extern "C" int ck_potrf(double* a, ck_i64 n, ck_i64 ld, void* ws, int* info, void* stream) {
+  CK_REQUIRE(n >= 0, "negative size");
+  CK_REQUIRE(info, "info is NULL");
+  cudaStream_t st = ck_stream(stream);
+  CK_CUDA(cudaMemsetAsync(info, 0, sizeof(int), st));
+  if (n == 0) return CK_OK;
+  CK_REQUIRE(a && ws, "null pointer");
+  CK_REQUIRE(ld >= n, "ld (%lld) < n (%lld)", (long long)ld, (long long)n);
+  double* xinv = static_cast<double*>(ws);
+  int rc;
+  for (ck_i64 k0 = 0, kb = 0; k0 < n; k0 += CK_NB, ++kb) {
+    const int nb = (int)((n - k0 < CK_NB) ? n - k0 : CK_NB);
+    const ck_i64 k1 = k0 + nb;
+    double* xk = xinv + kb * CK_NB * CK_NB;
+    if ((rc = potf2_launch(a + k0 * ld + k0, ld, nb, xk, info, (int)k0, st))) return rc;
+    if (k1 < n) {
+      GemmArgs t;  // panel: A[k1:, k0:k1] <- A[k1:, k0:k1] X_k^T   (in place, one column tile)
+      t.A = a + k1 * ld + k0; t.lda = ld;
+      t.B = xk; t.ldb = CK_NB;
+      t.C = a + k1 * ld + k0; t.ldc = ld;
+      t.M = n - k1; t.N = nb; t.K = nb; t.mode = 0; t.lower_only = 0;
+      if ((rc = gemm_launch<2, 4>(t, st))) return rc;
+      GemmArgs s;  // trailing: A[k1:, k1:] -= P P^T, lower tiles
+      s.A = a + k1 * ld + k0; s.lda = ld;
+      s.B = a + k1 * ld + k0; s.ldb = ld;
+      s.C = a + k1 * ld + k1; s.ldc = ld;
+      s.M = n - k1; s.N = n - k1; s.K = nb; s.mode = 1; s.lower_only = 1;
+      if ((rc = gemm_launch<4, 2>(s, st))) return rc;
+    }
+  }
+  return CK_OK;
+}
+
+extern "C" int ck_trsm_lower(const double* l, ck_i64 n, ck_i64 ld, const void* ws, double* rhs, ck_i64 nrhs, ck_i64 ld_rhs,
+                             void* stream) {
+  CK_REQUIRE(n >= 0 && nrhs >= 0, "negative size");
+  if (n == 0 || nrhs == 0) return CK_OK;
+  CK_REQUIRE(l && ws && rhs, "null pointer");
+  CK_REQUIRE(ld >= n && ld_rhs >= n, "leading dimension too small");
+  cudaStream_t st = ck_stream(stream);
+  const double* xinv = static_cast<const double*>(ws);
+  int rc;
+  for (ck_i64 k0 = 0, kb = 0; k0 < n; k0 += CK_NB, ++kb) {
+    const int nb = (int)((n - k0 < CK_NB) ? n - k0 : CK_NB);
+    const ck_i64 k1 = k0 + nb;
+    GemmArgs t;  // V[:, k] = R[:, k] X_k^T  (in place)
+    t.A = rhs + k0; t.lda = ld_rhs;
+    t.B = xinv + kb * CK_NB * CK_NB; t.ldb = CK_NB;
+    t.C = rhs + k0; t.ldc = ld_rhs;
+    t.M = nrhs; t.N = nb; t.K = nb; t.mode = 0; t.lower_only = 0;
+    if ((rc = gemm_launch<2, 4>(t, st))) return rc;
+    if (k1 < n) {
+      GemmArgs u;  // R[:, k1:] -= V[:, k] L[k1:, k]^T
+      u.A = rhs + k0; u.lda = ld_rhs;
+      u.B = l + k1 * ld + k0; u.ldb = ld;
+      u.C = rhs + k1; u.ldc = ld_rhs;
+      u.M = nrhs; u.N = n - k1; u.K = nb; u.mode = 1; u.lower_only = 0;
+      if ((rc = gemm_launch<4, 2>(u, st))) return rc;
+    }
+  }
+  return CK_OK;
+}
+
+extern "C" int ck_potrs_predict(const double* l, ck_i64 n, ck_i64 ld, const void* ws, double* cpd, ck_i64 m, ck_i64 ld_c,
+                                const double* z, double c0, double* pred, double* var, void* stream) {
+  CK_REQUIRE(n >= 0 && m >= 0, "negative size");
+  if (n == 0) return CK_OK;
+  CK_REQUIRE(l && ws && cpd && z, "null pointer");
+  CK_REQUIRE(m == 0 || (pred && var), "null output");
+  cudaStream_t st = ck_stream(stream);
+  CK_CUDA(cudaMemcpyAsync(cpd + m * ld_c, z, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  int rc = ck_trsm_lower(l, n, ld, ws, cpd, m + 1, ld_c, stream);
+  if (rc) return rc;
+  if (m > 0) {
+    ck_predict_rows_kernel<<<(unsigned)m, 256, 0, st>>>(cpd, ld_c, n, cpd + m * ld_c, c0, pred, var);
+    CK_LAUNCH_CHECK();
+  }
+  return CK_OK;
+}
+
+extern "C" int ck_logdet(const double* l, ck_i64 n, ck_i64 ld, double* out, void* stream) {
+  CK_REQUIRE(n >= 0 && l && out, "bad argument");
+  ck_diag_reduce_kernel<<<1, 1024, 0, ck_stream(stream)>>>(l, ld, n, 0, out);
+  CK_LAUNCH_CHECK();
+  return CK_OK;
+}
+
+extern "C" int ck_nll(const double* xy0, ck_i64 n0, const double* xy1, ck_i64 n1, const double* params, int n_procs,
+                      int metric, const double* z, double* sigma, ck_i64 ld, void* ws, double* scratch, double* out,
+                      int* info, void* stream) {
+  if (n_procs == 1) n1 = 0;
+  const ck_i64 n = n0 + n1;
+  CK_REQUIRE(z && sigma && ws && scratch && out && info, "null pointer");
+  cudaStream_t st = ck_stream(stream);
+  int rc;
+  if ((rc = ck_joint_cov(xy0, n0, xy1, n1, params, n_procs, metric, sigma, ld, stream))) return rc;
+  if ((rc = ck_potrf(sigma, n, ld, ws, info, stream))) return rc;
+  CK_CUDA(cudaMemcpyAsync(scratch, z, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  if ((rc = ck_trsm_lower(sigma, n, ld, ws, scratch, 1, n, stream))) return rc;
+  ck_diag_reduce_kernel<<<1, 1024, 0, st>>>(scratch, 0, n, 1, out + 1);
+  ck_diag_reduce_kernel<<<1, 1024, 0, st>>>(sigma, ld, n, 0, out + 2);
+  ck_nll_combine_kernel<<<1, 1, 0, st>>>(out, n);
+  CK_LAUNCH_CHECK();
+  return CK_OK;
+}

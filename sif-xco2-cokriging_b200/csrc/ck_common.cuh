@@ -1,0 +1,46 @@
+// ck_common.cuh -- internal helpers shared by the translation units of libcokrig_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/cokrig.h"
+#include "ck_math.cuh"
+#include "ck_matern_setup.h"
+
+#define CK_NB 128  // Cholesky panel width == diagonal block size == GEMM K depth per step
+
+void ck_set_error(const char* fmt, ...);
+
+#define CK_REQUIRE(cond, ...)      \
+  do {                             \
+    if (!(cond)) {                 \
+      ck_set_error(__VA_ARGS__);   \
+      return CK_ERR_ARG;           \
+    }                              \
+  } while (0)
+
+#define CK_CUDA(call)                                                                   \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess) {                                                            \
+      ck_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      return CK_ERR_CUDA;                                                               \
+    }                                                                                   \
+  } while (0)
+
+#define CK_LAUNCH_CHECK() CK_CUDA(cudaGetLastError())
+
+// The reference's parameter matrices unpacked from the flat vector (src/model.py:130-152).
+struct CkParams {
+  int n_procs;
+  double sigma[2], nugget[2];
+  double nu[2][2], len_scale[2][2];  // symmetric fill
+  double rho01;
+  double sigma_prod;  // np.nanprod(sigma matrix) -- product of ALL marginal sigmas (src/model.py:203-207)
+};
+
+int ck_unpack_params(const double* params, int n_procs, CkParams* out);
+// Block (i, j) of the joint model: i == j -> covariance(i, ., use_nugget), else cross_covariance(i, j, .)
+int ck_block_matern(const CkParams& p, int i, int j, int use_nugget, CkMatern* out);
+
+static inline cudaStream_t ck_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }

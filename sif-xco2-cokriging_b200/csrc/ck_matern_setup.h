@@ -1,0 +1,69 @@
+// ck_matern_setup.h -- host-side preparation of the per-block Matern constants (CkMatern).
+// Pure host C++ (no CUDA); shared by the C-ABI (ck_api.cu) and the host validation build
+// (tests/hostmath).  Parameter meaning follows src/model.py:188-207 of the reference.
+#pragma once
+#include <math.h>
+#include "ck_math.cuh"
+
+// Taylor coefficients of 1/Gamma(1+z) about z = 0 (generated with mpmath at 40 digits).
+static const double CK_RGAMMA1P[27] = {
+    1.0,
+    0.5772156649015328606065121,
+    -0.6558780715202538810770195,
+    -0.04200263503409523552900393,
+    0.1665386113822914895017008,
+    -0.0421977345555443367482083,
+    -0.009621971527876973562114922,
+    0.00721894324666309954239501,
+    -0.001165167591859065112113971,
+    -0.00021524167411495097281573,
+    0.0001280502823881161861531986,
+    -0.00002013485478078823865568939,
+    -0.000001250493482142670657345359,
+    0.00000113302723198169588237413,
+    -0.0000002056338416977607103450154,
+    6.116095104481415817862499e-9,
+    5.002007644469222930055665e-9,
+    -1.181274570487020144588127e-9,
+    1.04342671169110051049154e-10,
+    7.782263439905071254049937e-12,
+    -3.696805618642205708187816e-12,
+    5.100370287454475979015481e-13,
+    -2.05832605356650678322243e-14,
+    -5.348122539423017982370017e-15,
+    1.226778628238260790158894e-15,
+    -1.181259301697458769513765e-16,
+    1.186692254751600332579777e-18};
+
+// returns 0 on success, -1 on invalid parameters
+static inline int ck_matern_setup(CkMatern* P, double scale, double nu, double len_scale, double nugget) {
+  if (!(nu > 0.0) || !(len_scale > 0.0) || !(nu < 1.0e3)) return -1;
+  P->scale = scale;
+  P->nugget = nugget;
+  P->len_scale = len_scale;
+  P->nu = nu;
+  P->sqrt2nu = sqrt(2.0 * nu);
+  P->lc = (1.0 - nu) * log(2.0) - lgamma(nu);
+  if (nu == 0.5) P->mode = CK_NU_HALF;
+  else if (nu == 1.5) P->mode = CK_NU_3HALF;
+  else if (nu == 2.5) P->mode = CK_NU_5HALF;
+  else if (nu == 3.5) P->mode = CK_NU_7HALF;
+  else P->mode = CK_NU_GENERIC;
+  const int nl = (int)(nu + 0.5);
+  const long double mu = (long double)nu - (long double)nl;
+  const long double m2 = mu * mu;
+  long double even = 0.0L, odd = 0.0L;  // sum c_2k mu^2k, sum c_(2k+1) mu^2k
+  for (int k = 26; k >= 0; k -= 2) even = even * m2 + (long double)CK_RGAMMA1P[k];
+  odd = 0.0L;
+  for (int k = 25; k >= 1; k -= 2) odd = odd * m2 + (long double)CK_RGAMMA1P[k];
+  P->nl = nl;
+  P->mu = (double)mu;
+  P->mu2 = (double)m2;
+  P->gam1 = (double)(-odd);             // (1/G(1-mu) - 1/G(1+mu)) / (2 mu)
+  P->gam2 = (double)even;               // (1/G(1-mu) + 1/G(1+mu)) / 2
+  P->gampl = (double)(even + mu * odd); // 1/Gamma(1+mu)
+  P->gammi = (double)(even - mu * odd); // 1/Gamma(1-mu)
+  const long double pm = 3.14159265358979323846264338327950288L * mu;
+  P->pimu = (fabsl(pm) < 1.0e-9L) ? 1.0 : (double)(pm / sinl(pm));
+  return 0;
+}

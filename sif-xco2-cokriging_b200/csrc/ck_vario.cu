@@ -1,0 +1,329 @@
+// ck_vario.cu -- K2: empirical (cross-)semivariogram pair binning for sm_100a.
+//
+// All pairs are visited tile by tile (VA x VB points per CTA, coordinates prepared once in shared
+// memory).  Inside a CTA every lane owns a PRIVATE histogram column in shared memory
+// (layout [warp][bin][lane]: conflict-free, no atomics), so each partial sum is built by exactly one
+// thread in a fixed order; lanes, warps and tiles are then combined by fixed-shape trees.  The
+// decomposition depends only on (na, nb, n_bins) -- never on the device or the launch -- hence the
+// FP64 sums are bit-reproducible and the integer counts are exact.
+// Bin decision = pandas.cut(include_lowest=True) on host-supplied edges: bin k <=> e[k] < d <= e[k+1],
+// d == e[0] -> bin 0, d > e[n_bins] dropped (src/fields.py:208-222).
+#include "ck_common.cuh"
+
+constexpr int VA = 128;  // rows of A per tile
+constexpr int VB = 256;  // rows of B per tile
+constexpr int V_MAX_WARPS = 8;
+constexpr int V_SMEM_BUDGET = 200 * 1024;  // histogram bytes per CTA
+
+struct VarioGeom {
+  long long ta, tb;  // tiles along A, B
+};
+static inline VarioGeom vario_geom(long long na, long long nb) {
+  VarioGeom g;
+  g.ta = (na + VA - 1) / VA;
+  g.tb = (nb + VB - 1) / VB;
+  return g;
+}
+static inline int vario_warps(int n_bins) {
+  int w = V_SMEM_BUDGET / (n_bins * 32 * 12);
+  if (w > V_MAX_WARPS) w = V_MAX_WARPS;
+  // power of two so that the warp tree has a fixed shape
+  int p = 1;
+  while (p * 2 <= w) p *= 2;
+  return w >= 1 ? p : 0;
+}
+
+__device__ __forceinline__ unsigned long long dbits(double d) { return (unsigned long long)__double_as_longlong(d); }
+
+// ------------------------------------------------------------------------------------------------
+// pass 1: min non-zero distance, max distance and number of pairs with d <= max_dist
+// (min / max are order-free, so plain atomics on the bit patterns of non-negative doubles are exact)
+template <int METRIC>
+__global__ void __launch_bounds__(256) ck_vario_minmax_kernel(const double* __restrict__ xya, long long na,
+                                                              const double* __restrict__ xyb, long long nb,
+                                                              int same_field, double max_dist,
+                                                              unsigned long long* __restrict__ out) {
+  const long long a0 = (long long)blockIdx.y * VA, b0 = (long long)blockIdx.x * VB;
+  if (same_field && b0 + VB - 1 <= a0) return;  // tile entirely on/below the diagonal
+  __shared__ CkPoint pa[VA], pb[VB];
+  __shared__ unsigned long long smin[8], smax[8], scnt[8];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if (t < VA && a0 + t < na) pa[t] = ck_prepare_point(METRIC, xya[2 * (a0 + t)], xya[2 * (a0 + t) + 1]);
+  if (b0 + t < nb) pb[t] = ck_prepare_point(METRIC, xyb[2 * (b0 + t)], xyb[2 * (b0 + t) + 1]);
+  __syncthreads();
+  unsigned long long mn = 0x7FF0000000000000ULL, mx = 0ULL, cnt = 0ULL;
+  bool any = false;
+  for (int ia = warp; ia < VA; ia += 8) {
+    const long long ga = a0 + ia;
+    if (ga >= na) break;
+    const CkPoint p = pa[ia];
+#pragma unroll 4
+    for (int q = 0; q < VB / 32; ++q) {
+      const int ib = lane + 32 * q;
+      const long long gb = b0 + ib;
+      if (gb < nb && (!same_field || gb > ga)) {
+        const double d = ck_dist<METRIC>(p, pb[ib]);
+        if (d <= max_dist) {
+          const unsigned long long u = dbits(d);
+          ++cnt;
+          if (d > 0.0 && u < mn) mn = u;
+          if (!any || u > mx) mx = u;
+          any = true;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long omn = __shfl_xor_sync(0xffffffffu, mn, o);
+    const unsigned long long omx = __shfl_xor_sync(0xffffffffu, mx, o);
+    const unsigned long long oc = __shfl_xor_sync(0xffffffffu, cnt, o);
+    mn = omn < mn ? omn : mn;
+    mx = omx > mx ? omx : mx;
+    cnt += oc;
+  }
+  if (lane == 0) { smin[warp] = mn; smax[warp] = mx; scnt[warp] = cnt; }
+  __syncthreads();
+  if (t == 0) {
+    for (int w = 1; w < 8; ++w) {
+      mn = smin[w] < mn ? smin[w] : mn;
+      mx = smax[w] > mx ? smax[w] : mx;
+      cnt += scnt[w];
+    }
+    if (cnt) {
+      atomicMin(out + 0, mn);
+      atomicMax(out + 1, mx);
+      atomicAdd(out + 2, cnt);
+    }
+  }
+}
+
+__global__ void ck_vario_minmax_init_kernel(unsigned long long* out) {
+  out[0] = 0x7FF0000000000000ULL;  // +inf
+  out[1] = 0ULL;
+  out[2] = 0ULL;
+}
+__global__ void ck_vario_minmax_final_kernel(unsigned long long* out) {
+  const unsigned long long cnt = out[2];
+  double* o = reinterpret_cast<double*>(out);
+  if (cnt == 0) o[1] = -__longlong_as_double(0x7FF0000000000000LL);
+  o[2] = (double)cnt;
+}
+
+extern "C" int ck_vario_minmax(const double* xya, ck_i64 na, const double* xyb, ck_i64 nb, int metric, int same_field,
+                               double max_dist, double* out, void* stream) {
+  CK_REQUIRE(na >= 0 && nb >= 0 && out, "bad argument");
+  CK_REQUIRE(metric == CK_METRIC_EUCLID || metric == CK_METRIC_HAVERSINE, "bad metric %d", metric);
+  CK_REQUIRE(!same_field || na == nb, "same_field needs na == nb");
+  cudaStream_t st = ck_stream(stream);
+  unsigned long long* o = reinterpret_cast<unsigned long long*>(out);
+  ck_vario_minmax_init_kernel<<<1, 1, 0, st>>>(o);
+  if (na > 0 && nb > 0) {
+    CK_REQUIRE(xya && xyb, "null pointer");
+    const VarioGeom g = vario_geom(na, nb);
+    CK_REQUIRE(g.ta <= 65535, "na too large");
+    dim3 grid((unsigned)g.tb, (unsigned)g.ta);
+    if (metric == CK_METRIC_HAVERSINE) ck_vario_minmax_kernel<CK_METRIC_HAVERSINE><<<grid, 256, 0, st>>>(xya, na, xyb, nb, same_field, max_dist, o);
+    else ck_vario_minmax_kernel<CK_METRIC_EUCLID><<<grid, 256, 0, st>>>(xya, na, xyb, nb, same_field, max_dist, o);
+  }
+  ck_vario_minmax_final_kernel<<<1, 1, 0, st>>>(o);
+  CK_LAUNCH_CHECK();
+  return CK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass 2: binning
+struct VarioBinArgs {
+  const double* xya; const double* va; long long na; double mean_a;
+  const double* xyb; const double* vb; long long nb; double mean_b;
+  int same_field, covariogram;
+  double max_dist;
+  const double* edges;  // device copy inside the workspace
+  int n_bins;
+  double e1, inv_w;     // uniform-width guess: k = (d - e1) * inv_w + 1
+  double* tile_sums;                // [tile][bin]
+  unsigned int* tile_counts;        // [tile][bin]
+};
+
+template <int METRIC>
+__global__ void __launch_bounds__(256) ck_vario_bin_kernel(VarioBinArgs g, int nwarps) {
+  extern __shared__ __align__(16) unsigned char vsm[];
+  const int nb_ = g.n_bins;
+  double* hsum = reinterpret_cast<double*>(vsm);                                  // [warp][bin][lane]
+  unsigned int* hcnt = reinterpret_cast<unsigned int*>(hsum + (size_t)nwarps * nb_ * 32);  // [warp][bin][lane]
+  double* edges = reinterpret_cast<double*>(hcnt + (size_t)nwarps * nb_ * 32);   // n_bins + 1
+  __shared__ CkPoint pa[VA], pb[VB];
+  __shared__ double ra[VA], rb[VB];
+  const long long a0 = (long long)blockIdx.y * VA, b0 = (long long)blockIdx.x * VB;
+  const long long tile = (long long)blockIdx.y * gridDim.x + blockIdx.x;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int nthreads = nwarps * 32;
+  const bool skip = g.same_field && (b0 + VB - 1 <= a0);
+  if (skip) {  // still publish zeros so that the tile tree reads defined values
+    for (int k = t; k < nb_; k += nthreads) {
+      g.tile_sums[tile * nb_ + k] = 0.0;
+      g.tile_counts[tile * nb_ + k] = 0u;
+    }
+    return;
+  }
+  for (int i = t; i < nwarps * nb_ * 32; i += nthreads) {
+    hsum[i] = 0.0;
+    hcnt[i] = 0u;
+  }
+  for (int i = t; i <= nb_; i += nthreads) edges[i] = g.edges[i];
+  for (int i = t; i < VA; i += nthreads)
+    if (a0 + i < g.na) {
+      pa[i] = ck_prepare_point(METRIC, g.xya[2 * (a0 + i)], g.xya[2 * (a0 + i) + 1]);
+      ra[i] = g.va[a0 + i] - g.mean_a;
+    }
+  for (int i = t; i < VB; i += nthreads)
+    if (b0 + i < g.nb) {
+      pb[i] = ck_prepare_point(METRIC, g.xyb[2 * (b0 + i)], g.xyb[2 * (b0 + i) + 1]);
+      rb[i] = g.vb[b0 + i] - g.mean_b;
+    }
+  __syncthreads();
+  double* mysum = hsum + (size_t)warp * nb_ * 32 + lane;
+  unsigned int* mycnt = hcnt + (size_t)warp * nb_ * 32 + lane;
+  const double e_last = edges[nb_], e_first = edges[0];
+  for (int ia = warp; ia < VA; ia += nwarps) {
+    const long long ga = a0 + ia;
+    if (ga >= g.na) break;
+    const CkPoint p = pa[ia];
+    const double r = ra[ia];
+#pragma unroll 4
+    for (int q = 0; q < VB / 32; ++q) {
+      const int ib = lane + 32 * q;
+      const long long gb = b0 + ib;
+      if (gb < g.nb && (!g.same_field || gb > ga)) {
+        const double d = ck_dist<METRIC>(p, pb[ib]);
+        if (d <= g.max_dist && d <= e_last && d >= e_first) {
+          int k = (int)((d - g.e1) * g.inv_w) + 1;
+          k = k < 0 ? 0 : (k > nb_ - 1 ? nb_ - 1 : k);
+          while (k > 0 && d <= edges[k]) --k;
+          while (k < nb_ - 1 && d > edges[k + 1]) ++k;
+          double v;
+          if (g.covariogram) v = r * rb[ib];
+          else { const double df = r - rb[ib]; v = 0.5 * (df * df); }
+          mysum[k * 32] += v;
+          mycnt[k * 32] += 1u;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // lanes -> (fixed xor tree), warps -> (fixed tree), one thread writes the tile partial
+  for (int k = warp; k < nb_; k += nwarps) {
+    double s[V_MAX_WARPS];
+    unsigned int c[V_MAX_WARPS];
+    for (int w = 0; w < nwarps; ++w) {
+      double sv = hsum[((size_t)w * nb_ + k) * 32 + lane];
+      unsigned int cv = hcnt[((size_t)w * nb_ + k) * 32 + lane];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        sv += __shfl_xor_sync(0xffffffffu, sv, o);
+        cv += __shfl_xor_sync(0xffffffffu, cv, o);
+      }
+      s[w] = sv;
+      c[w] = cv;
+    }
+    for (int h = 1; h < nwarps; h <<= 1)
+      for (int w = 0; w + h < nwarps; w += 2 * h) {
+        s[w] += s[w + h];
+        c[w] += c[w + h];
+      }
+    if (lane == 0) {
+      g.tile_sums[tile * nb_ + k] = s[0];
+      g.tile_counts[tile * nb_ + k] = c[0];
+    }
+  }
+}
+
+// one CTA per bin: strided per-thread partials over tiles (fixed order), shared-memory tree
+__global__ void __launch_bounds__(256) ck_vario_tile_reduce_kernel(const double* __restrict__ tile_sums,
+                                                                   const unsigned int* __restrict__ tile_counts,
+                                                                   long long ntiles, int n_bins,
+                                                                   unsigned long long* __restrict__ counts,
+                                                                   double* __restrict__ sums) {
+  __shared__ double rs[256];
+  __shared__ unsigned long long rc[256];
+  const int k = blockIdx.x, t = threadIdx.x;
+  double s = 0.0;
+  unsigned long long c = 0ULL;
+  for (long long i = t; i < ntiles; i += 256) {
+    s += tile_sums[i * n_bins + k];
+    c += tile_counts[i * n_bins + k];
+  }
+  rs[t] = s;
+  rc[t] = c;
+  __syncthreads();
+  for (int h = 128; h > 0; h >>= 1) {
+    if (t < h) {
+      rs[t] += rs[t + h];
+      rc[t] += rc[t + h];
+    }
+    __syncthreads();
+  }
+  if (t == 0) {
+    sums[k] = rs[0];
+    counts[k] = rc[0];
+  }
+}
+
+static inline size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+extern "C" size_t ck_vario_bin_workspace_bytes(ck_i64 na, ck_i64 nb, int n_bins) {
+  if (na <= 0 || nb <= 0 || n_bins <= 0) return 256;
+  const VarioGeom g = vario_geom(na, nb);
+  const size_t tiles = (size_t)g.ta * g.tb;
+  return align256((size_t)(n_bins + 1) * 8) + align256(tiles * n_bins * 8) + align256(tiles * n_bins * 4);
+}
+
+extern "C" int ck_vario_bin(const double* xya, const double* va, ck_i64 na, double mean_a, const double* xyb,
+                            const double* vb, ck_i64 nb, double mean_b, int metric, int same_field, int covariogram,
+                            double max_dist, const double* edges, int n_bins, unsigned long long* counts, double* sums,
+                            void* ws, void* stream) {
+  CK_REQUIRE(na >= 0 && nb >= 0, "negative size");
+  CK_REQUIRE(n_bins >= 1 && edges && counts && sums && ws, "bad argument");
+  CK_REQUIRE(metric == CK_METRIC_EUCLID || metric == CK_METRIC_HAVERSINE, "bad metric %d", metric);
+  CK_REQUIRE(!same_field || na == nb, "same_field needs na == nb");
+  for (int k = 0; k < n_bins; ++k) CK_REQUIRE(edges[k] < edges[k + 1], "edges must be strictly ascending");
+  const int nwarps = vario_warps(n_bins);
+  if (nwarps < 1) { ck_set_error("n_bins=%d exceeds the shared-memory histogram capacity", n_bins); return CK_ERR_UNSUPPORTED; }
+  cudaStream_t st = ck_stream(stream);
+  if (na == 0 || nb == 0) {
+    CK_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * n_bins, st));
+    CK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * n_bins, st));
+    return CK_OK;
+  }
+  CK_REQUIRE(xya && va && xyb && vb, "null pointer");
+  const VarioGeom geo = vario_geom(na, nb);
+  CK_REQUIRE(geo.ta <= 65535, "na too large");
+  const size_t tiles = (size_t)geo.ta * geo.tb;
+  unsigned char* w = static_cast<unsigned char*>(ws);
+  double* edges_dev = reinterpret_cast<double*>(w);
+  double* tile_sums = reinterpret_cast<double*>(w + align256((size_t)(n_bins + 1) * 8));
+  unsigned int* tile_counts = reinterpret_cast<unsigned int*>(w + align256((size_t)(n_bins + 1) * 8) + align256(tiles * n_bins * 8));
+  CK_CUDA(cudaMemcpyAsync(edges_dev, edges, sizeof(double) * (n_bins + 1), cudaMemcpyHostToDevice, st));
+  VarioBinArgs g;
+  g.xya = xya; g.va = va; g.na = na; g.mean_a = mean_a;
+  g.xyb = xyb; g.vb = vb; g.nb = nb; g.mean_b = mean_b;
+  g.same_field = same_field; g.covariogram = covariogram; g.max_dist = max_dist;
+  g.edges = edges_dev; g.n_bins = n_bins;
+  g.e1 = n_bins >= 2 ? edges[1] : edges[0];
+  const double wdt = n_bins >= 2 ? (edges[n_bins] - edges[1]) / (double)(n_bins - 1) : 0.0;
+  g.inv_w = wdt > 0.0 ? 1.0 / wdt : 0.0;
+  g.tile_sums = tile_sums; g.tile_counts = tile_counts;
+  const size_t smem = (size_t)nwarps * n_bins * 32 * 12 + (size_t)(n_bins + 1) * 8 + 16;
+  dim3 grid((unsigned)geo.tb, (unsigned)geo.ta);
+  if (metric == CK_METRIC_HAVERSINE) {
+    CK_CUDA(cudaFuncSetAttribute(ck_vario_bin_kernel<CK_METRIC_HAVERSINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ck_vario_bin_kernel<CK_METRIC_HAVERSINE><<<grid, nwarps * 32, smem, st>>>(g, nwarps);
+  } else {
+    CK_CUDA(cudaFuncSetAttribute(ck_vario_bin_kernel<CK_METRIC_EUCLID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ck_vario_bin_kernel<CK_METRIC_EUCLID><<<grid, nwarps * 32, smem, st>>>(g, nwarps);
+  }
+  CK_LAUNCH_CHECK();
+  ck_vario_tile_reduce_kernel<<<n_bins, 256, 0, st>>>(tile_sums, tile_counts, (long long)tiles, n_bins, counts, sums);
+  CK_LAUNCH_CHECK();
+  return CK_OK;
+}

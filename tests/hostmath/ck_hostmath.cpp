@@ -1,0 +1,35 @@
+// Host instantiation of csrc/ck_math.cuh for NUMERICAL VALIDATION ONLY (tests tier, no GPU).
+// Built by __graft_entry__.build() / tests/conftest.py with
+//   g++ -O2 -ffp-contract=off -shared -fPIC ck_hostmath.cpp -o _ck_hostmath.so
+// It lets the CPU test tier compare the exact scalar code the sm_100a kernels inline against
+// scipy/mpmath.  It is NOT part of the product library and is never used as a fallback.
+#include "../../sif-xco2-cokriging_b200/csrc/ck_math.cuh"
+#include "../../sif-xco2-cokriging_b200/csrc/ck_matern_setup.h"
+
+extern "C" {
+
+int ckh_besselk(double nu, const double* x, long n, double* out) {
+  CkMatern P;
+  if (ck_matern_setup(&P, 1.0, nu, 1.0, 0.0)) return -1;
+  for (long i = 0; i < n; ++i) out[i] = ck_besselk(P, x[i]);
+  return 0;
+}
+
+int ckh_matern_cov(double scale, double nu, double len_scale, double nugget, const double* h, long n, double* out) {
+  CkMatern P;
+  if (ck_matern_setup(&P, scale, nu, len_scale, nugget)) return -1;
+  for (long i = 0; i < n; ++i) out[i] = ck_matern_cov_dyn(P, h[i]);
+  return 0;
+}
+
+int ckh_distance(int metric, const double* X1, long n1, const double* X2, long n2, double* out) {
+  for (long i = 0; i < n1; ++i) {
+    const CkPoint p = ck_prepare_point(metric, X1[2 * i], X1[2 * i + 1]);
+    for (long j = 0; j < n2; ++j) {
+      const CkPoint q = ck_prepare_point(metric, X2[2 * j], X2[2 * j + 1]);
+      out[i * n2 + j] = metric == CK_METRIC_HAVERSINE ? ck_dist_haversine(p, q) : ck_dist_euclid(p, q);
+    }
+  }
+  return 0;
+}
+}
