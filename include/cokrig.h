@@ -45,6 +45,8 @@ typedef int64_t ck_i64;
 
 int ck_version(void);
 const char* ck_last_error(void);
+/* Number of kernels this library has launched in the calling process so far (monotonic). */
+long long ck_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * K1  Matern (cross-)covariance assembly
@@ -133,12 +135,28 @@ int ck_nll(const double* xy0_dev, ck_i64 n0, const double* xy1_dev, ck_i64 n1, c
  * K2  empirical (cross-)semivariogram pair binning
  * ---------------------------------------------------------------------------------------------- */
 
-/* Pass 1: over all pairs (a < b if same_field, else all a, b) with d <= max_dist:
+/* Guard band.  Haversine distances from the device differ from sklearn's (glibc sin/asin) by a few
+ * ulp, so a pair sitting within ~8 ulp of a decision boundary (max_dist, a bin edge, the extrema that
+ * define the edges) could be decided differently.  Those pairs are not decided on the device: they are
+ * returned as index pairs and the host re-evaluates them with libm (fields._host_distance), which
+ * makes bin centres and bin counts bit-identical to the reference.  Euclidean distances are
+ * bit-identical to scipy.cdist and need no guard (lists stay empty). */
+
+size_t ck_vario_minmax_workspace_bytes(ck_i64 na, ck_i64 nb);
+
+/* Pass 1: over all pairs (a < b if same_field, else all a, b) with d <= max_dist (+ guard band):
  *   out_dev[0] = min{d : d > 0} (+inf if none), out_dev[1] = max d (-inf if none),
- *   out_dev[2] = number of retained pairs (as double, exact below 2^53).
+ *   out_dev[2] = number of such pairs (as double, exact below 2^53);  ws_dev keeps per-tile extrema.
  * Replaces the two reductions of fields._construct_variogram_bins (src/fields.py:394-395). */
 int ck_vario_minmax(const double* xya_dev, ck_i64 na, const double* xyb_dev, ck_i64 nb, int metric, int same_field,
-                    double max_dist, double* out_dev, void* stream);
+                    double max_dist, double* out_dev, void* ws_dev, void* stream);
+
+/* Index pairs (a, b) with 0 < d <= lo or d >= hi (and d <= max_dist + guard): the candidates for the
+ * exact extrema.  pairs_dev holds 2*capacity entries; *count_dev may exceed capacity (then only the
+ * first `capacity` pairs were stored).  ws_dev is the workspace filled by ck_vario_minmax. */
+int ck_vario_candidates(const double* xya_dev, ck_i64 na, const double* xyb_dev, ck_i64 nb, int metric, int same_field,
+                        double max_dist, double lo, double hi, const void* ws_dev, ck_i64* pairs_dev, ck_i64 capacity,
+                        unsigned long long* count_dev, void* stream);
 
 size_t ck_vario_bin_workspace_bytes(ck_i64 na, ck_i64 nb, int n_bins);
 
@@ -147,11 +165,14 @@ size_t ck_vario_bin_workspace_bytes(ck_i64 na, ck_i64 nb, int n_bins);
  * d > edges[n_bins] dropped.  Cloud value 0.5 (ra - rb)^2 (covariogram == 0) or ra * rb, with
  * ra = va - mean_a, rb = vb - mean_b (src/fields.py:378-386).  counts_dev: n_bins uint64 (bit-exact);
  * sums_dev: n_bins FP64 sums accumulated in a fixed, launch-geometry-independent order.
+ * flagged_dev (may be NULL: no guard): pairs inside the guard band are appended there instead of
+ * being binned (2*flag_capacity entries, *flag_count_dev as in ck_vario_candidates).
  * Replaces _variogram_cloud + pd.cut + groupby.agg  (src/fields.py:192-222). */
 int ck_vario_bin(const double* xya_dev, const double* va_dev, ck_i64 na, double mean_a, const double* xyb_dev,
                  const double* vb_dev, ck_i64 nb, double mean_b, int metric, int same_field, int covariogram,
                  double max_dist, const double* edges /*HOST*/, int n_bins, unsigned long long* counts_dev,
-                 double* sums_dev, void* ws_dev, void* stream);
+                 double* sums_dev, ck_i64* flagged_dev, ck_i64 flag_capacity, unsigned long long* flag_count_dev,
+                 void* ws_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K4  batched local-neighbourhood cokriging (point prediction)

@@ -381,3 +381,35 @@ def loocv_reference(p: Params, i: int, coords_main, values_main, metric):
         pr, sd, _ = joint_predict(p, i, coords_main, values_main, coords_main[i][ix], metric, cv_ix=ix)
         preds.append(pr[0]); sds.append(sd[0])
     return np.array(preds), np.array(sds)
+
+
+# --------------------------------------------------------------------------- CPU baseline helper
+def joint_predict_phases(p: Params, i: int, coords_main, values_main, pcoords, metric) -> dict:
+    """src/joint_prediction.py:50-78 executed phase by phase with wall-clock times (bench.py's
+    cpu_baseline / --impl reference legs).  Same calls as ``joint_predict``."""
+    import time
+    t = {}
+    t0 = time.perf_counter()
+    c_pp = pred_cov(p, i, pcoords, metric)
+    c_dp = pred_cross_cov(p, i, coords_main, pcoords, metric)
+    sigma = joint_cov(p, coords_main, metric)
+    t["assemble_s"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    try:
+        cho_factor(np.vstack([np.hstack([c_pp, c_dp.T]), np.hstack([c_dp, sigma])]), overwrite_a=True)
+    except LinAlgError:
+        pass
+    t["verify_s"] = time.perf_counter() - t0
+    z = np.hstack(values_main)
+    t0 = time.perf_counter()
+    fac = cho_factor(sigma, lower=True, overwrite_a=True, check_finite=False)
+    t["factor_s"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    w = cho_solve(fac, c_dp.copy(), overwrite_b=True, check_finite=False).T
+    var = np.diagonal(c_pp - np.matmul(w, c_dp))
+    pred = np.matmul(w, z)
+    with np.errstate(invalid="ignore"):
+        err = np.nan_to_num(np.sqrt(var))
+    t["solve_s"] = time.perf_counter() - t0
+    t["pred"], t["pred_err"] = pred, err
+    return t

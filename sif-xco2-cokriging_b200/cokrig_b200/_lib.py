@@ -41,6 +41,7 @@ _hp = POINTER(c_double)  # host double arrays
 SIGNATURES = {
     "ck_version": (c_int, []),
     "ck_last_error": (c_char_p, []),
+    "ck_launch_count": (ctypes.c_longlong, []),
     "ck_matern_eval": (c_int, [_dp, c_int64, c_double, c_double, c_double, c_double, _dp, c_void_p]),
     "ck_distance_block": (c_int, [_dp, c_int64, _dp, c_int64, c_int, _dp, c_int64, c_void_p]),
     "ck_matern_block": (c_int, [_dp, c_int64, _dp, c_int64, c_int, c_double, c_double, c_double, c_double,
@@ -56,10 +57,13 @@ SIGNATURES = {
     "ck_logdet": (c_int, [_dp, c_int64, c_int64, _dp, c_void_p]),
     "ck_nll": (c_int, [_dp, c_int64, _dp, c_int64, _hp, c_int, c_int, _dp, _dp, c_int64, _dp, _dp, _dp, _dp,
                        c_void_p]),
-    "ck_vario_minmax": (c_int, [_dp, c_int64, _dp, c_int64, c_int, c_int, c_double, _dp, c_void_p]),
+    "ck_vario_minmax_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "ck_vario_minmax": (c_int, [_dp, c_int64, _dp, c_int64, c_int, c_int, c_double, _dp, _dp, c_void_p]),
+    "ck_vario_candidates": (c_int, [_dp, c_int64, _dp, c_int64, c_int, c_int, c_double, c_double, c_double, _dp, _dp,
+                                    c_int64, _dp, c_void_p]),
     "ck_vario_bin_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int]),
     "ck_vario_bin": (c_int, [_dp, _dp, c_int64, c_double, _dp, _dp, c_int64, c_double, c_int, c_int, c_int,
-                             c_double, _hp, c_int, _dp, _dp, _dp, c_void_p]),
+                             c_double, _hp, c_int, _dp, _dp, _dp, c_int64, _dp, _dp, c_void_p]),
     "ck_local_predict_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "ck_local_count": (c_int, [_dp, c_int64, _dp, c_int64, _dp, c_int64, c_int, c_int, c_int, c_double, c_int,
                                _dp, c_void_p]),

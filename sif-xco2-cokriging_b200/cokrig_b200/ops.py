@@ -229,30 +229,65 @@ def gaussian_nll(coords: Sequence[torch.Tensor], z: torch.Tensor, params, n_proc
 
 
 # ------------------------------------------------------------------------------------------------ K2
-def vario_minmax(Xa: torch.Tensor, Xb: torch.Tensor, metric: int, same_field: bool, max_dist: float):
-    """(min non-zero distance, max distance, number of pairs) over pairs with d <= max_dist."""
+VARIO_GUARD = 1.8e-15  # must match CK_VARIO_GUARD (csrc/ck_vario.cu)
+VARIO_LIST_CAPACITY = 1 << 16
+
+
+def _read_pairs(pairs: torch.Tensor, count: torch.Tensor, what: str):
+    n = int(count.item())
+    if n > pairs.shape[0]:
+        raise RuntimeError(f"{what}: {n} ambiguous pairs exceed the list capacity {pairs.shape[0]} "
+                           "(degenerate geometry: many pairs exactly on a decision boundary)")
+    return pairs[:n].cpu().numpy()
+
+
+def vario_extrema(Xa: torch.Tensor, Xb: torch.Tensor, metric: int, same_field: bool, max_dist: float) -> dict:
+    """Device pass 1: {'min': min non-zero distance, 'max': max distance, 'count': pairs} over pairs
+    with d <= max_dist, plus 'candidates': (a, b) index pairs inside the guard band of the extrema
+    (haversine only; None for the exact Euclidean metric)."""
+    na, nb = Xa.shape[0], Xb.shape[0]
     out = torch.empty(3, dtype=F64, device=Xa.device)
-    check(lib.ck_vario_minmax(_ptr(Xa), Xa.shape[0], _ptr(Xb), Xb.shape[0], metric, int(same_field), float(max_dist),
-                              _ptr(out), _stream()), "ck_vario_minmax")
+    ws = torch.empty(int(lib.ck_vario_minmax_workspace_bytes(na, nb)) // 8 + 1, dtype=F64, device=Xa.device)
+    check(lib.ck_vario_minmax(_ptr(Xa), na, _ptr(Xb), nb, metric, int(same_field), float(max_dist), _ptr(out), _ptr(ws),
+                              _stream()), "ck_vario_minmax")
     mn, mx, cnt = out.cpu().tolist()
-    return mn, mx, int(cnt)
+    res = {"min": mn, "max": mx, "count": int(cnt), "candidates": None}
+    if metric == METRIC_HAVERSINE and cnt > 0:
+        pairs = torch.empty((VARIO_LIST_CAPACITY, 2), dtype=torch.int64, device=Xa.device)
+        count = torch.zeros(1, dtype=torch.int64, device=Xa.device)
+        lo, hi = mn * (1.0 + 2 * VARIO_GUARD), mx * (1.0 - 2 * VARIO_GUARD)
+        check(lib.ck_vario_candidates(_ptr(Xa), na, _ptr(Xb), nb, metric, int(same_field), float(max_dist), lo, hi,
+                                      _ptr(ws), _ptr(pairs), VARIO_LIST_CAPACITY, _ptr(count), _stream()),
+              "ck_vario_candidates")
+        res["candidates"] = _read_pairs(pairs, count, "variogram extrema")
+    return res
+
+
+def vario_minmax(Xa: torch.Tensor, Xb: torch.Tensor, metric: int, same_field: bool, max_dist: float):
+    r = vario_extrema(Xa, Xb, metric, same_field, max_dist)
+    return r["min"], r["max"], r["count"]
 
 
 def vario_bin(Xa: torch.Tensor, va: torch.Tensor, mean_a: float, Xb: torch.Tensor, vb: torch.Tensor, mean_b: float,
-              metric: int, same_field: bool, covariogram: bool, max_dist: float, edges: np.ndarray):
-    """Per-bin (counts int64 ndarray, sums float64 ndarray) with pandas.cut(include_lowest=True) semantics."""
+              metric: int, same_field: bool, covariogram: bool, max_dist: float, edges: np.ndarray, guard: bool = True):
+    """Device pass 2: per-bin (counts int64, sums float64, flagged) with pandas.cut(include_lowest=True)
+    semantics; `flagged` = (a, b) index pairs left undecided inside the guard band (or None)."""
     e = np.ascontiguousarray(np.asarray(edges, dtype=np.float64))
     n_bins = e.size - 1
     na, nb = Xa.shape[0], Xb.shape[0]
-    nbytes = int(lib.ck_vario_bin_workspace_bytes(na, nb, n_bins))
-    ws = torch.empty(nbytes // 8 + 1, dtype=F64, device=Xa.device)
+    ws = torch.empty(int(lib.ck_vario_bin_workspace_bytes(na, nb, n_bins)) // 8 + 1, dtype=F64, device=Xa.device)
     counts = torch.empty(n_bins, dtype=torch.int64, device=Xa.device)
     sums = torch.empty(n_bins, dtype=F64, device=Xa.device)
+    use_guard = guard and metric == METRIC_HAVERSINE
+    pairs = torch.empty((VARIO_LIST_CAPACITY, 2), dtype=torch.int64, device=Xa.device) if use_guard else None
+    count = torch.zeros(1, dtype=torch.int64, device=Xa.device)
     check(lib.ck_vario_bin(_ptr(Xa), _ptr(va), na, float(mean_a), _ptr(Xb), _ptr(vb), nb, float(mean_b), metric,
                            int(same_field), int(covariogram), float(max_dist),
-                           e.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), n_bins, _ptr(counts), _ptr(sums), _ptr(ws),
-                           _stream()), "ck_vario_bin")
-    return counts.cpu().numpy(), sums.cpu().numpy()
+                           e.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), n_bins, _ptr(counts), _ptr(sums),
+                           _ptr(pairs), VARIO_LIST_CAPACITY if use_guard else 0, _ptr(count), _ptr(ws), _stream()),
+          "ck_vario_bin")
+    flagged = _read_pairs(pairs, count, "variogram binning") if use_guard else None
+    return counts.cpu().numpy(), sums.cpu().numpy(), flagged
 
 
 # ------------------------------------------------------------------------------------------------ K4

@@ -516,6 +516,6 @@ extern "C" int ck_nll(const double* xy0, ck_i64 n0, const double* xy1, ck_i64 n1
   ck_diag_reduce_kernel<<<1, 1024, 0, st>>>(scratch, 0, n, 1, out + 1);
   ck_diag_reduce_kernel<<<1, 1024, 0, st>>>(sigma, ld, n, 0, out + 2);
   ck_nll_combine_kernel<<<1, 1, 0, st>>>(out, n);
-  CK_LAUNCH_CHECK();
+  CK_LAUNCH_CHECK_N(3);
   return CK_OK;
 }

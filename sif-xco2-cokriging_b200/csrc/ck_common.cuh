@@ -28,7 +28,14 @@ void ck_set_error(const char* fmt, ...);
     }                                                                                   \
   } while (0)
 
-#define CK_LAUNCH_CHECK() CK_CUDA(cudaGetLastError())
+// every kernel launch of the library is counted (bench.py reports it as `gpu_launches`)
+void ck_count_launches(int n);
+#define CK_LAUNCH_CHECK_N(n)        \
+  do {                              \
+    ck_count_launches(n);           \
+    CK_CUDA(cudaGetLastError());    \
+  } while (0)
+#define CK_LAUNCH_CHECK() CK_LAUNCH_CHECK_N(1)
 
 // The reference's parameter matrices unpacked from the flat vector (src/model.py:130-152).
 struct CkParams {

@@ -17,6 +17,11 @@ void ck_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 extern "C" const char* ck_last_error(void) { return g_err; }
+
+#include <atomic>
+static std::atomic<long long> g_launches{0};
+void ck_count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+extern "C" long long ck_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 extern "C" int ck_version(void) { return 100; }
 
 int ck_unpack_params(const double* v, int n_procs, CkParams* p) {

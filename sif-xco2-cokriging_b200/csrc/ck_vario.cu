@@ -42,9 +42,14 @@ template <int METRIC>
 __global__ void __launch_bounds__(256) ck_vario_minmax_kernel(const double* __restrict__ xya, long long na,
                                                               const double* __restrict__ xyb, long long nb,
                                                               int same_field, double max_dist,
-                                                              unsigned long long* __restrict__ out) {
+                                                              unsigned long long* __restrict__ out,
+                                                              unsigned long long* __restrict__ tile_mm) {
   const long long a0 = (long long)blockIdx.y * VA, b0 = (long long)blockIdx.x * VB;
-  if (same_field && b0 + VB - 1 <= a0) return;  // tile entirely on/below the diagonal
+  const long long tile = (long long)blockIdx.y * gridDim.x + blockIdx.x;
+  if (same_field && b0 + VB - 1 <= a0) {  // tile entirely on/below the diagonal
+    if (threadIdx.x == 0) { tile_mm[2 * tile] = 0x7FF0000000000000ULL; tile_mm[2 * tile + 1] = 0ULL; }
+    return;
+  }
   __shared__ CkPoint pa[VA], pb[VB];
   __shared__ unsigned long long smin[8], smax[8], scnt[8];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -63,7 +68,7 @@ __global__ void __launch_bounds__(256) ck_vario_minmax_kernel(const double* __re
       const long long gb = b0 + ib;
       if (gb < nb && (!same_field || gb > ga)) {
         const double d = ck_dist<METRIC>(p, pb[ib]);
-        if (d <= max_dist) {
+        if (d <= max_dist) {  // max_dist already widened by the guard band for inexact metrics
           const unsigned long long u = dbits(d);
           ++cnt;
           if (d > 0.0 && u < mn) mn = u;
@@ -90,10 +95,50 @@ __global__ void __launch_bounds__(256) ck_vario_minmax_kernel(const double* __re
       mx = smax[w] > mx ? smax[w] : mx;
       cnt += scnt[w];
     }
+    tile_mm[2 * tile] = mn;
+    tile_mm[2 * tile + 1] = cnt ? mx : 0ULL;
     if (cnt) {
       atomicMin(out + 0, mn);
       atomicMax(out + 1, mx);
       atomicAdd(out + 2, cnt);
+    }
+  }
+}
+
+// Pairs whose device distance is within the guard band of the extrema: the host re-evaluates them
+// with libm so that bin centres/edges carry exactly the reference's bits.  Only tiles whose own
+// extrema reach the bands do any work.
+template <int METRIC>
+__global__ void __launch_bounds__(256) ck_vario_candidates_kernel(const double* __restrict__ xya, long long na,
+                                                                  const double* __restrict__ xyb, long long nb,
+                                                                  int same_field, double dlim, double lo, double hi,
+                                                                  const unsigned long long* __restrict__ tile_mm,
+                                                                  ck_i64* __restrict__ pairs, long long capacity,
+                                                                  unsigned long long* __restrict__ count) {
+  const long long a0 = (long long)blockIdx.y * VA, b0 = (long long)blockIdx.x * VB;
+  const long long tile = (long long)blockIdx.y * gridDim.x + blockIdx.x;
+  const double tmn = __longlong_as_double((long long)tile_mm[2 * tile]);
+  const double tmx = __longlong_as_double((long long)tile_mm[2 * tile + 1]);
+  if (!(tmn <= lo) && !(tmx >= hi)) return;
+  __shared__ CkPoint pa[VA], pb[VB];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if (t < VA && a0 + t < na) pa[t] = ck_prepare_point(METRIC, xya[2 * (a0 + t)], xya[2 * (a0 + t) + 1]);
+  if (b0 + t < nb) pb[t] = ck_prepare_point(METRIC, xyb[2 * (b0 + t)], xyb[2 * (b0 + t) + 1]);
+  __syncthreads();
+  for (int ia = warp; ia < VA; ia += 8) {
+    const long long ga = a0 + ia;
+    if (ga >= na) break;
+    const CkPoint p = pa[ia];
+    for (int q = 0; q < VB / 32; ++q) {
+      const int ib = lane + 32 * q;
+      const long long gb = b0 + ib;
+      if (gb < nb && (!same_field || gb > ga)) {
+        const double d = ck_dist<METRIC>(p, pb[ib]);
+        if (d <= dlim && ((d > 0.0 && d <= lo) || d >= hi)) {
+          const unsigned long long pos = atomicAdd(count, 1ULL);
+          if ((long long)pos < capacity) { pairs[2 * pos] = ga; pairs[2 * pos + 1] = gb; }
+        }
+      }
     }
   }
 }
@@ -110,8 +155,21 @@ __global__ void ck_vario_minmax_final_kernel(unsigned long long* out) {
   o[2] = (double)cnt;
 }
 
+// relative half-width of the guard band around decision boundaries (~8 ulp); haversine only --
+// Euclidean distances are bit-identical to scipy's and need no guard
+#define CK_VARIO_GUARD 1.8e-15
+static inline double vario_dlim(int metric, double max_dist) {
+  return metric == CK_METRIC_HAVERSINE ? max_dist * (1.0 + CK_VARIO_GUARD) : max_dist;
+}
+
+extern "C" size_t ck_vario_minmax_workspace_bytes(ck_i64 na, ck_i64 nb) {
+  if (na <= 0 || nb <= 0) return 256;
+  const VarioGeom g = vario_geom(na, nb);
+  return (size_t)g.ta * g.tb * 16 + 256;
+}
+
 extern "C" int ck_vario_minmax(const double* xya, ck_i64 na, const double* xyb, ck_i64 nb, int metric, int same_field,
-                               double max_dist, double* out, void* stream) {
+                               double max_dist, double* out, void* ws, void* stream) {
   CK_REQUIRE(na >= 0 && nb >= 0 && out, "bad argument");
   CK_REQUIRE(metric == CK_METRIC_EUCLID || metric == CK_METRIC_HAVERSINE, "bad metric %d", metric);
   CK_REQUIRE(!same_field || na == nb, "same_field needs na == nb");
@@ -119,14 +177,35 @@ extern "C" int ck_vario_minmax(const double* xya, ck_i64 na, const double* xyb, 
   unsigned long long* o = reinterpret_cast<unsigned long long*>(out);
   ck_vario_minmax_init_kernel<<<1, 1, 0, st>>>(o);
   if (na > 0 && nb > 0) {
-    CK_REQUIRE(xya && xyb, "null pointer");
+    CK_REQUIRE(xya && xyb && ws, "null pointer");
     const VarioGeom g = vario_geom(na, nb);
     CK_REQUIRE(g.ta <= 65535, "na too large");
     dim3 grid((unsigned)g.tb, (unsigned)g.ta);
-    if (metric == CK_METRIC_HAVERSINE) ck_vario_minmax_kernel<CK_METRIC_HAVERSINE><<<grid, 256, 0, st>>>(xya, na, xyb, nb, same_field, max_dist, o);
-    else ck_vario_minmax_kernel<CK_METRIC_EUCLID><<<grid, 256, 0, st>>>(xya, na, xyb, nb, same_field, max_dist, o);
+    unsigned long long* mm = static_cast<unsigned long long*>(ws);
+    const double dlim = vario_dlim(metric, max_dist);
+    if (metric == CK_METRIC_HAVERSINE) ck_vario_minmax_kernel<CK_METRIC_HAVERSINE><<<grid, 256, 0, st>>>(xya, na, xyb, nb, same_field, dlim, o, mm);
+    else ck_vario_minmax_kernel<CK_METRIC_EUCLID><<<grid, 256, 0, st>>>(xya, na, xyb, nb, same_field, dlim, o, mm);
   }
   ck_vario_minmax_final_kernel<<<1, 1, 0, st>>>(o);
+  CK_LAUNCH_CHECK_N((na > 0 && nb > 0) ? 3 : 2);
+  return CK_OK;
+}
+
+extern "C" int ck_vario_candidates(const double* xya, ck_i64 na, const double* xyb, ck_i64 nb, int metric, int same_field,
+                                   double max_dist, double lo, double hi, const void* ws, ck_i64* pairs, ck_i64 capacity,
+                                   unsigned long long* count, void* stream) {
+  CK_REQUIRE(na >= 0 && nb >= 0 && pairs && count && capacity >= 0, "bad argument");
+  CK_REQUIRE(metric == CK_METRIC_EUCLID || metric == CK_METRIC_HAVERSINE, "bad metric %d", metric);
+  cudaStream_t st = ck_stream(stream);
+  CK_CUDA(cudaMemsetAsync(count, 0, sizeof(unsigned long long), st));
+  if (na == 0 || nb == 0) return CK_OK;
+  CK_REQUIRE(xya && xyb && ws, "null pointer");
+  const VarioGeom g = vario_geom(na, nb);
+  dim3 grid((unsigned)g.tb, (unsigned)g.ta);
+  const unsigned long long* mm = static_cast<const unsigned long long*>(ws);
+  const double dlim = vario_dlim(metric, max_dist);
+  if (metric == CK_METRIC_HAVERSINE) ck_vario_candidates_kernel<CK_METRIC_HAVERSINE><<<grid, 256, 0, st>>>(xya, na, xyb, nb, same_field, dlim, lo, hi, mm, pairs, capacity, count);
+  else ck_vario_candidates_kernel<CK_METRIC_EUCLID><<<grid, 256, 0, st>>>(xya, na, xyb, nb, same_field, dlim, lo, hi, mm, pairs, capacity, count);
   CK_LAUNCH_CHECK();
   return CK_OK;
 }
@@ -143,6 +222,9 @@ struct VarioBinArgs {
   double e1, inv_w;     // uniform-width guess: k = (d - e1) * inv_w + 1
   double* tile_sums;                // [tile][bin]
   unsigned int* tile_counts;        // [tile][bin]
+  // pairs within the guard band of an edge / of max_dist are not binned but appended here (host decides)
+  ck_i64* flagged; long long flag_capacity; unsigned long long* flag_count;
+  double guard, dlim;
 };
 
 template <int METRIC>
@@ -196,11 +278,22 @@ __global__ void __launch_bounds__(256) ck_vario_bin_kernel(VarioBinArgs g, int n
       const long long gb = b0 + ib;
       if (gb < g.nb && (!g.same_field || gb > ga)) {
         const double d = ck_dist<METRIC>(p, pb[ib]);
-        if (d <= g.max_dist && d <= e_last && d >= e_first) {
+        if (d <= g.dlim && d >= e_first) {
           int k = (int)((d - g.e1) * g.inv_w) + 1;
           k = k < 0 ? 0 : (k > nb_ - 1 ? nb_ - 1 : k);
           while (k > 0 && d <= edges[k]) --k;
           while (k < nb_ - 1 && d > edges[k + 1]) ++k;
+          if (g.flagged) {
+            const double band = g.guard * d;
+            const bool near = fabs(d - g.max_dist) <= g.guard * g.max_dist || (k > 0 && d - edges[k] <= band) ||
+                              fabs(edges[k + 1] - d) <= band;
+            if (near) {
+              const unsigned long long pos = atomicAdd(g.flag_count, 1ULL);
+              if ((long long)pos < g.flag_capacity) { g.flagged[2 * pos] = ga; g.flagged[2 * pos + 1] = gb; }
+              continue;
+            }
+          }
+          if (!(d <= g.max_dist && d <= e_last)) continue;
           double v;
           if (g.covariogram) v = r * rb[ib];
           else { const double df = r - rb[ib]; v = 0.5 * (df * df); }
@@ -281,7 +374,8 @@ extern "C" size_t ck_vario_bin_workspace_bytes(ck_i64 na, ck_i64 nb, int n_bins)
 extern "C" int ck_vario_bin(const double* xya, const double* va, ck_i64 na, double mean_a, const double* xyb,
                             const double* vb, ck_i64 nb, double mean_b, int metric, int same_field, int covariogram,
                             double max_dist, const double* edges, int n_bins, unsigned long long* counts, double* sums,
-                            void* ws, void* stream) {
+                            ck_i64* flagged, ck_i64 flag_capacity, unsigned long long* flag_count, void* ws,
+                            void* stream) {
   CK_REQUIRE(na >= 0 && nb >= 0, "negative size");
   CK_REQUIRE(n_bins >= 1 && edges && counts && sums && ws, "bad argument");
   CK_REQUIRE(metric == CK_METRIC_EUCLID || metric == CK_METRIC_HAVERSINE, "bad metric %d", metric);
@@ -290,6 +384,8 @@ extern "C" int ck_vario_bin(const double* xya, const double* va, ck_i64 na, doub
   const int nwarps = vario_warps(n_bins);
   if (nwarps < 1) { ck_set_error("n_bins=%d exceeds the shared-memory histogram capacity", n_bins); return CK_ERR_UNSUPPORTED; }
   cudaStream_t st = ck_stream(stream);
+  CK_REQUIRE(!flagged || (flag_count && flag_capacity >= 0), "flag_count is NULL");
+  if (flag_count) CK_CUDA(cudaMemsetAsync(flag_count, 0, sizeof(unsigned long long), st));
   if (na == 0 || nb == 0) {
     CK_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * n_bins, st));
     CK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * n_bins, st));
@@ -313,6 +409,9 @@ extern "C" int ck_vario_bin(const double* xya, const double* va, ck_i64 na, doub
   const double wdt = n_bins >= 2 ? (edges[n_bins] - edges[1]) / (double)(n_bins - 1) : 0.0;
   g.inv_w = wdt > 0.0 ? 1.0 / wdt : 0.0;
   g.tile_sums = tile_sums; g.tile_counts = tile_counts;
+  const bool guard = flagged && metric == CK_METRIC_HAVERSINE;  // Euclidean distances are exact: no guard
+  g.flagged = guard ? flagged : nullptr; g.flag_capacity = flag_capacity; g.flag_count = flag_count;
+  g.guard = CK_VARIO_GUARD; g.dlim = guard ? vario_dlim(metric, max_dist) : max_dist;
   const size_t smem = (size_t)nwarps * n_bins * 32 * 12 + (size_t)(n_bins + 1) * 8 + 16;
   dim3 grid((unsigned)geo.tb, (unsigned)geo.ta);
   if (metric == CK_METRIC_HAVERSINE) {

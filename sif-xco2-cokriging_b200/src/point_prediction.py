@@ -1,0 +1,150 @@
+"""Drop-in replacement for the reference's ``src/point_prediction.py`` (local-neighbourhood simple cokriging).
+
+Signatures follow /root/reference/src/point_prediction.py:21-355.  The per-target Python loop of the
+reference (``DataFrame.apply`` -> ``_local_prediction``: neighbour masks, ``np.ix_`` gathers, two
+k x k Cholesky factorisations; :127-249) is replaced by ONE batched device call
+(``ck_local_count`` + ``ck_local_predict``): one CTA per target selects the neighbours, re-computes
+the local covariance from coordinates, factors and solves.  ``partitions`` is accepted and ignored
+(the reference forks a multiprocessing.Pool, :69-81; a single device batch needs no processes).
+
+Same outputs and corner cases: ``(nan, nan)`` with a warning when no datum lies within ``max_dist``
+or when the local matrix is not positive definite; ``pred_err = nanmax(sqrt(c0 - w.c), 0)``;
+"Invalid model" warning when the augmented matrix is not PD (kriging variance <= 0, the Schur
+complement of the reference's (1+k)^2 check).  ``Sigma`` (dict of host blocks "00", "01", "11") is
+assembled lazily on first access, since the device path does not need it.
+"""
+from __future__ import annotations
+
+import warnings
+from multiprocessing import cpu_count
+
+import numpy as np
+import pandas as pd
+
+from _backend import ops
+from fields import MultiField, distance_matrix  # noqa: F401
+from model import MultivariateMatern
+
+# number of partitions for parallel computation (kept for API compatibility; unused on the device)
+NCORES = cpu_count()
+
+
+class Predictor:
+    """Multivariate prediction framework."""
+
+    def __init__(self, mod: MultivariateMatern, mf: MultiField, covariates=None, dist_units: str = "km",
+                 fast_dist: bool = True) -> None:
+        if mod.n_procs != mf.n_procs:
+            raise ValueError("Number of theoretical processes different from empirical processes.")
+        self.n_procs = mod.n_procs
+        self.mod = mod
+        self.mf = mf
+        self.covariates = covariates
+        self.dist_units = dist_units
+        self.fast_dist = fast_dist
+        self._Sigma = None
+        self.cv = False  # placeholder for cross-validation
+
+    def _metric(self) -> int:
+        return ops.metric_id(self.dist_units, self.fast_dist)
+
+    @property
+    def Sigma(self) -> dict:
+        """Upper-triangular block dict of the joint covariance on ``coords_main`` (host arrays)."""
+        if self._Sigma is None:
+            self._Sigma = self._cov_blocks()
+        return self._Sigma
+
+    def _cov_blocks(self) -> dict:
+        """Each block of the block-covariance matrix (within a process or between processes)."""
+        p = self.mod.params
+        metric = self._metric()
+        X = [ops.coords_to_device(np.asarray(f.coords_main, dtype=float)) for f in self.mf.fields]
+        blocks = dict()
+        for i in range(self.n_procs):
+            for j in range(i, self.n_procs):
+                if i == j:
+                    b = ops.matern_block(X[i], X[i], metric, p.sigma.values[i, i] ** 2, p.nu.values[i, i],
+                                         p.len_scale.values[i, i], p.nugget.values[i, i], symmetric=True)
+                else:
+                    scale = p.rho.values[i, j] * float(np.nanprod(p.sigma.values))
+                    b = ops.matern_block(X[i], X[j], metric, scale, p.nu.values[i, j], p.len_scale.values[i, j], 0.0)
+                blocks[f"{i}{j}"] = b.cpu().numpy()
+        return blocks
+
+    def _predict_chunk(self, df_chunk: pd.DataFrame, c0: float, max_dist: float):
+        """Batched local prediction for all rows of `df_chunk` (adds ``pred`` and ``pred_err``)."""
+        pc = df_chunk.iloc[:, :2].values.astype(float)
+        coords = [ops.coords_to_device(np.asarray(f.coords_main, dtype=float)) for f in self.mf.fields]
+        values = [ops.to_device(np.asarray(f.values_main, dtype=float)) for f in self.mf.fields]
+        pred, sd, k, info = ops.local_predict(coords, values, ops.coords_to_device(pc), self.mod.params.get_values(),
+                                              self.n_procs, self.i, self._metric(), max_dist, cv=self.cv)
+        for row in np.flatnonzero(k == 0):
+            warnings.warn(f"No data within maximum distance {max_dist} at location {pc[row]}.")
+        for row in np.flatnonzero(info == -1):
+            warnings.warn(f"Invalid model at prediction location {pc[row]}. This can happen at data locations.")
+        if (info > 0).any():
+            warnings.warn("Local covariance matrix not positive definte; returning NaN.")
+        self.last_neighbour_counts = k
+        df_chunk[["pred", "pred_err"]] = np.column_stack([pred, sd])
+        return df_chunk
+
+    def predict_frame(self, i: int, pcoords, max_dist: float = 1e3) -> pd.DataFrame:
+        """DataFrame with the columns of `pcoords` plus ``pred`` and ``pred_err`` (no xarray needed)."""
+        self.i = i
+        c0 = self.mod.covariance(self.i, 0, use_nugget=True)[0]
+        if not isinstance(pcoords, pd.DataFrame):
+            pcoords = pd.DataFrame(np.atleast_2d(np.asarray(pcoords, dtype=float)), columns=["d1", "d2"])
+        return self._predict_chunk(pcoords.copy(), c0, max_dist)
+
+    def __call__(self, i: int, pcoords: pd.DataFrame, max_dist: float = 1e3, partitions: int = None,
+                 postprocess: bool = True):
+        """Multivariate local prediction at every location of `pcoords` ([[lat, lon]] or [[x, y]]).
+
+        max_dist: data farther than this from a target are ignored; partitions: ignored (kept for
+        compatibility); postprocess: back-transform to the original data scale.
+        Returns an xarray Dataset with ``pred`` and ``pred_err``."""
+        df_pred = self.predict_frame(i, pcoords, max_dist=max_dist)
+        if postprocess:
+            return self._postprocess_predictions(df_pred)
+        ds = df_pred.set_index(pcoords.columns.values.tolist()).to_xarray()
+        try:
+            np.isnan(self.mf.fields[self.i].timestamp)
+            return ds
+        except TypeError:
+            return ds.assign_coords(coords={"time": np.datetime64(self.mf.fields[self.i].timestamp)})
+
+    def _postprocess_predictions(self, df: pd.DataFrame):
+        """Back-transform to the original data scale (shared with the joint predictor; host, xarray)."""
+        import joint_prediction
+        return joint_prediction.Predictor._postprocess_predictions(self, df)
+
+    def cross_validation_frame(self, i: int, max_dist: float = 1e3) -> pd.DataFrame:
+        """LOOCV on the standardised scale: columns d1, d2, data, pred, residual, pred_err."""
+        self.cv = True
+        f = self.mf.fields[i]
+        data = pd.DataFrame(np.hstack((f.coords_main, np.atleast_2d(f.values_main).T)), columns=["d1", "d2", "data"])
+        df = self.predict_frame(i, data[["d1", "d2"]], max_dist=max_dist)
+        df["data"] = data["data"].values
+        df["residual"] = df["data"] - df["pred"]
+        return df[["d1", "d2", "data", "pred", "residual", "pred_err"]]
+
+    def cross_validation(self, i: int, max_dist: float = 1e3, partitions: int = None, postprocess: bool = True):
+        """Leave-one-out cross-validation at each data location of process i (value withheld via the
+        ``0 < d`` neighbour rule, :140-142).  Returns a data frame with the prediction residuals."""
+        df = self.cross_validation_frame(i, max_dist=max_dist)
+        if not postprocess:
+            return df
+        df = df.rename(columns={"d1": "lat", "d2": "lon"})
+        ds = self._postprocess_predictions(df[["lat", "lon", "pred", "pred_err"]].copy())
+        out = (ds.to_dataframe().reset_index().dropna(subset=["pred"])
+               .merge(df[["lat", "lon", "data"]], on=["lat", "lon"], how="outer"))
+        out["residual"] = out["data"] - out["pred"]
+        return out[["lat", "lon", "data", "pred", "residual", "pred_err"]]
+
+
+def prediction_coords(extents: tuple = (-125, -65, 22, 58), lon_res: float = 0.5, lat_res: float = 0.5) -> np.ndarray:
+    """Prediction coordinates (land only)."""
+    from data_utils import GridConfig, land_grid
+    grid = GridConfig(extents=extents, lon_res=lon_res, lat_res=lat_res)
+    return land_grid(grid).reset_index()[["lat", "lon"]]

@@ -1,0 +1,72 @@
+"""The C-ABI library loads and exports every symbol include/cokrig.h declares; the ctypes binding
+declares exactly the same set; host-only entry points behave; no compute call is made (CPU tier)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+HEADER = os.path.join(ROOT, "include", "cokrig.h")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ck_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_expected_entry_points():
+    names = declared_symbols()
+    for must in ("ck_matern_block", "ck_joint_cov", "ck_cross_cov", "ck_potrf", "ck_potrs_predict", "ck_vario_minmax",
+                 "ck_vario_bin", "ck_local_predict", "ck_nll", "ck_matern_eval", "ck_distance_block"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol():
+    from cokrig_b200 import _lib
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [n for n in declared_symbols() if not hasattr(lib, n)]
+    assert not missing, f"declared in cokrig.h but not exported: {missing}"
+
+
+def test_binding_covers_header_exactly():
+    from cokrig_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == declared_symbols()
+
+
+def test_host_only_entry_points():
+    from cokrig_b200 import _lib
+    assert _lib.lib.ck_version() >= 100
+    assert _lib.lib.ck_potrf_workspace_bytes(0) == 0
+    assert _lib.lib.ck_potrf_workspace_bytes(1) == 128 * 128 * 8
+    assert _lib.lib.ck_potrf_workspace_bytes(129) == 2 * 128 * 128 * 8
+    assert _lib.lib.ck_vario_bin_workspace_bytes(1000, 1000, 50) > 0
+    assert _lib.lib.ck_local_predict_workspace_bytes(10, 100) >= 10 * 102 * 112 * 8
+
+
+def test_argument_validation_without_gpu():
+    """Bad arguments are rejected before any CUDA call, with a message."""
+    from cokrig_b200 import _lib
+    rc = _lib.lib.ck_potrf(None, -1, 0, None, None, None)
+    assert rc == _lib.CK_ERR_ARG and "negative" in _lib.last_error()
+    bad = (ctypes.c_double * 11)(*([1.0] * 11))
+    rc = _lib.lib.ck_joint_cov(None, 4, None, 4, bad, 3, 0, None, 8, None)
+    assert rc == _lib.CK_ERR_UNSUPPORTED
+    with pytest.raises(_lib.CokrigError):
+        _lib.check(rc, "ck_joint_cov")
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product raises instead of computing on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    import numpy as np
+    from cokrig_b200 import ops
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.matern_eval(np.ones(3), 1.0, 1.5, 1.0)
+    import model
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model.MultivariateMatern().covariance(0, np.ones(3))

@@ -1,0 +1,128 @@
+"""Host-side logic of the drop-in modules that needs no GPU: parameter containers, bin construction,
+stat_tools, simulation grid, metric mapping -- checked against fixtures produced by the reference
+and (when the reference is present) against the live reference objects."""
+import numpy as np
+import pandas as pd
+import pytest
+
+from conftest import golden
+
+
+def test_matern_params_api_matches_reference_fixture():
+    import model
+    g = golden("params_api")
+    p2, p1 = model.MaternParams(2), model.MaternParams(1)
+    assert list(p2.get_names()) == list(g["names2"]) and list(p1.get_names()) == list(g["names1"])
+    np.testing.assert_array_equal(p2.get_values().astype(float), g["values2"])
+    np.testing.assert_array_equal(p1.get_values().astype(float), g["values1"])
+    np.testing.assert_array_equal(np.array([list(b) for b in p2.get_bounds()], float), g["bounds2"])
+    for name in ("sigma", "nu", "rho"):
+        np.testing.assert_array_equal(getattr(p2, name).values, g[name + "2"])
+    np.testing.assert_array_equal(p1.rho.values, g["rho1"])
+    p2.set_values(g["set_vals"])
+    np.testing.assert_array_equal(p2.nu.values, g["nu_after"])
+    np.testing.assert_array_equal(p2.rho.values, g["rho_after"])
+    np.testing.assert_array_equal(p2.get_values().astype(float), g["set_vals"])
+    assert p2.n_params == 11 and p1.n_params == 4
+    with pytest.raises(ValueError):
+        p2.set_values(np.ones(4))
+    with pytest.raises(AttributeError):
+        p2.set_bounds(foo=(0, 1))
+    p2.set_bounds(len_scale=(1e-8, 1.5))
+    assert p2.to_dataframe().loc[5, "bounds"] == (1e-8, 1.5)
+    np.testing.assert_array_equal(p2.reset_values().get_values().astype(float), g["values2"])
+
+
+def test_params_live_reference(ref):
+    import model
+    for n in (1, 2):
+        a, b = model.MaternParams(n), ref.model.MaternParams(n)
+        pd.testing.assert_frame_equal(a.to_dataframe(), b.to_dataframe(), check_dtype=False)
+        for name in ("sigma", "nu", "len_scale", "nugget", "rho"):
+            np.testing.assert_array_equal(getattr(a, name).values, getattr(b, name).values)
+            assert getattr(a, name).get_names() == getattr(b, name).get_names()
+
+
+def test_bins_from_extrema_matches_reference_fixture():
+    import fields
+    g = golden("variogram_haversine_semivariogram")
+    for key in ("00", "01", "11"):
+        c = g["center" + key]
+        centers, edges = fields._bins_from_extrema(c[0], c[-1], int(g["n_bins"]))
+        np.testing.assert_array_equal(centers, c)
+        np.testing.assert_array_equal(edges, g["edges" + key])
+        assert edges[0] == 0 and len(edges) == len(centers) + 1
+
+
+def test_construct_variogram_bins_signature():
+    import fields
+    d = np.array([0.0, 2.0, 5.0, 9.0, 4.0])
+    centers, edges = fields._construct_variogram_bins(pd.DataFrame({"distance": d, "variogram": d}), 4)
+    np.testing.assert_allclose(centers, np.linspace(2, 9, 4))
+    assert edges[0] == 0 and len(edges) == 5
+
+
+def test_stat_tools_match_reference_fixture():
+    import stat_tools
+    g = golden("stat_tools")
+    np.testing.assert_allclose(stat_tools.simple_linear_regression(g["x"].copy()), g["slr"], rtol=1e-12, equal_nan=True)
+    z, slope = stat_tools.detrend(g["x"].copy())
+    np.testing.assert_allclose(z, g["detrended"], rtol=1e-10, atol=1e-12, equal_nan=True)
+    np.testing.assert_allclose(slope, g["slope"], rtol=1e-12)
+    assert abs(stat_tools.compute_xcor_1d(g["x"], g["y"], lag=0) - g["xcor0"]) < 1e-14
+    assert abs(stat_tools.compute_xcor_1d(g["x"], g["y"], lag=2) - g["xcor2"]) < 1e-14
+    assert np.isnan(stat_tools.compute_xcor_1d(g["x"], g["y"], lag=2, tau=100))
+    np.testing.assert_allclose(stat_tools.compute_xcor_nd(g["Z1"], g["Z2"], lag=1, tau=10), g["xcor_nd"], rtol=1e-13,
+                               equal_nan=True)
+    np.testing.assert_array_equal(stat_tools.get_count(g["Z1"]), g["count"])
+    allnan = np.full(5, np.nan)
+    assert stat_tools.detrend(allnan)[0] is allnan and np.isnan(stat_tools.detrend(allnan)[1])
+
+
+def test_cartesian_grid_layout():
+    import sim
+    g = golden("sim")
+    grid = sim.CartesianGrid(xcount=12, ycount=12)
+    np.testing.assert_array_equal(grid.coords.values, g["coords"])
+    assert list(grid.coords.columns) == ["x", "y"] and grid.count == 144
+
+
+def test_metric_mapping_and_errors():
+    from cokrig_b200 import ops, METRIC_EUCLID, METRIC_HAVERSINE
+    assert ops.metric_id("km", True) == METRIC_HAVERSINE
+    assert ops.metric_id(None, False) == METRIC_EUCLID
+    with pytest.raises(NotImplementedError):
+        ops.metric_id("km", False)
+    with pytest.raises(ValueError):
+        ops._params(np.ones(5), 2)
+    with pytest.raises(NotImplementedError):
+        ops._params(np.ones(5), 3)
+    assert ops.padded_ld(1) == 16 and ops.padded_ld(17) == 32 and ops.padded_ld(40000) == 40000
+
+
+def test_predictor_process_count_mismatch():
+    import fields, joint_prediction, model, point_prediction
+    mf = fields.MultiField.from_arrays([np.zeros((3, 2))], [np.zeros(3)])
+    for mod in (joint_prediction, point_prediction):
+        with pytest.raises(ValueError, match="Number of theoretical processes"):
+            mod.Predictor(model.MultivariateMatern(n_procs=2), mf)
+    vc = fields.VarioConfig(10, 5, n_procs=1)
+    est = fields.EmpiricalVariogram(pd.DataFrame(), vc, np.nan, [np.nan])
+    with pytest.raises(ValueError, match="Number of theoretical processes"):
+        model.MultivariateMatern(n_procs=2).fit(est)
+
+
+def test_multifield_from_arrays_shapes():
+    import fields
+    mf = fields.MultiField.from_arrays([np.zeros((4, 2)), np.ones((3, 2))], [np.arange(4.0), np.arange(3.0)])
+    assert mf.n_procs == 2 and mf.n_data == 7 and mf.fields[1].size == 3
+    assert mf.fields[0].coords_main is mf.fields[0].coords
+    assert np.isnan(mf.timestamp)
+
+
+def test_wls_cost_helpers():
+    import model
+    y, f, c = np.array([1.0, 2.0, 3.0]), np.array([1.5, 0.0, 2.0]), np.array([10.0, 20.0, 30.0])
+    assert model._wls(y[[0, 2]], f[[0, 2]], c[[0, 2]]) == pytest.approx(10 * (0.5 / 1.5) ** 2 + 30 * 0.25)
+    assert model.MultivariateMatern._weighted_least_squares(y, f, c) == pytest.approx(
+        10 * (0.5 / 1.5) ** 2 + 20 * 4.0 + 30 * 0.25)
