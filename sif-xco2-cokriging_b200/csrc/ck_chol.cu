@@ -13,6 +13,7 @@
 // registers (initialised from C so the update needs no separate epilogue read).
 // The triangular solve with many right-hand sides keeps the RHS TARGET-MAJOR (one right-hand side
 // per row) so that it is the same NT GEMM:  V[:, k] = R[:, k] X_k^T ;  R[:, k+1:] -= V[:, k] L[k+1:, k]^T.
+#include <stdlib.h>
 #include "ck_common.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -47,7 +48,9 @@ struct GemmArgs {
   double* C; long long ldc;        // M x N
   long long M, N, K;
   int mode;        // 0: C = A B^T, 1: C = C - A B^T
-  int lower_only;  // 1: C square, only tiles intersecting the lower triangle; entries with col > row not stored
+  int lower_only;  // 1: C square, triangular grid over the tiles intersecting the lower triangle;
+                   // 2: C rectangular (M >= N, diagonal at the top-left), 2-D grid, tiles above the diagonal exit;
+                   // in both cases entries with col > row are not stored
 };
 
 // CTA tile (32*WM) x (32*WN); each of the 8 warps owns a 32 x 32 sub-tile = 4 x 4 DMMA tiles.
@@ -57,7 +60,7 @@ __global__ void __launch_bounds__(G_THREADS, 2) ck_gemm_nt_kernel(GemmArgs g) {
   constexpr int STAGE_ELEMS = (BM + BN) * G_LDS;
   extern __shared__ __align__(16) double smem[];
   long long tm, tn;
-  if (g.lower_only) {
+  if (g.lower_only == 1) {
     // linear tile id -> (row tile tm, col tile tn) over the lower block-triangle; row tm has RB*(tm+1) tiles
     constexpr int RB = (BM >= BN) ? BM / BN : 1;
     const long long t = blockIdx.x;
@@ -69,6 +72,7 @@ __global__ void __launch_bounds__(G_THREADS, 2) ck_gemm_nt_kernel(GemmArgs g) {
   } else {
     tm = blockIdx.y;
     tn = blockIdx.x;
+    if (g.lower_only == 2 && tn * BN > tm * BM + BM - 1) return;  // rectangular C: tile entirely above the diagonal
   }
   const long long m0 = tm * BM, n0 = tn * BN;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -198,7 +202,7 @@ static int gemm_launch(const GemmArgs& g, cudaStream_t st) {
   }
   const long long tm = (g.M + BM - 1) / BM, tn = (g.N + BN - 1) / BN;
   dim3 grid;
-  if (g.lower_only) {
+  if (g.lower_only == 1) {
     constexpr int RB = (BM >= BN) ? BM / BN : 1;
     CK_REQUIRE(BM >= BN, "lower_only needs BM >= BN");
     long long tiles = RB * tm * (tm + 1) / 2;
@@ -414,6 +418,59 @@ static int potf2_launch(double* a, long long ld, int nb, double* x, int* info, i
   return CK_OK;
 }
 
+// Aggregation width (in 128-blocks) of the trailing updates.  The factorisation is recursive inside
+// an aggregate: panels are factored 128 columns at a time, but the O(N^3) trailing update is applied
+// once per aggregate with K = 128 * CK_AGG, which halves (quarters, ...) the number of passes over the
+// trailing matrix and amortises each tile's prologue/epilogue over a longer DMMA main loop.
+static int agg_blocks() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("CK_AGG_BLOCKS");
+    v = e ? atoi(e) : 4;
+    if (v < 1) v = 1;
+    if (v > 64) v = 64;
+  }
+  return v;
+}
+
+struct CholCtx {
+  double* a; ck_i64 n, ld; double* xinv; int* info; cudaStream_t st;
+  ck_i64 s(ck_i64 b) const { return b * CK_NB < n ? b * CK_NB : n; }  // first row/col of block b (clamped)
+};
+
+// factor the column blocks [b0, b1) for all rows below, assuming every update from blocks < b0 was applied
+static int factor_range(const CholCtx& c, ck_i64 b0, ck_i64 b1) {
+  int rc;
+  if (b1 - b0 == 1) {
+    const ck_i64 k0 = c.s(b0), k1 = c.s(b1);
+    const int nb = (int)(k1 - k0);
+    double* xk = c.xinv + b0 * CK_NB * CK_NB;
+    if ((rc = potf2_launch(c.a + k0 * c.ld + k0, c.ld, nb, xk, c.info, (int)k0, c.st))) return rc;
+    if (k1 < c.n) {
+      GemmArgs t;  // panel: A[k1:, k0:k1] <- A[k1:, k0:k1] X_k^T   (in place, one column tile)
+      t.A = c.a + k1 * c.ld + k0; t.lda = c.ld;
+      t.B = xk; t.ldb = CK_NB;
+      t.C = c.a + k1 * c.ld + k0; t.ldc = c.ld;
+      t.M = c.n - k1; t.N = nb; t.K = nb; t.mode = 0; t.lower_only = 0;
+      if ((rc = gemm_launch<2, 4>(t, c.st))) return rc;
+    }
+    return CK_OK;
+  }
+  const ck_i64 mid = b0 + (b1 - b0 + 1) / 2;
+  if ((rc = factor_range(c, b0, mid))) return rc;
+  const ck_i64 r0 = c.s(mid), cl = c.s(b0), ce = c.s(b1);
+  if (r0 < c.n) {
+    GemmArgs u;  // A[r0:, r0:ce] -= A[r0:, cl:r0] A[r0:ce, cl:r0]^T   (thin update inside the aggregate)
+    u.A = c.a + r0 * c.ld + cl; u.lda = c.ld;
+    u.B = c.a + r0 * c.ld + cl; u.ldb = c.ld;
+    u.C = c.a + r0 * c.ld + r0; u.ldc = c.ld;
+    u.M = c.n - r0; u.N = ce - r0; u.K = r0 - cl; u.mode = 1; u.lower_only = 2;
+    if ((rc = gemm_launch<4, 2>(u, c.st))) return rc;
+    if ((rc = factor_range(c, mid, b1))) return rc;
+  }
+  return CK_OK;
+}
+
 extern "C" int ck_potrf(double* a, ck_i64 n, ck_i64 ld, void* ws, int* info, void* stream) {
   CK_REQUIRE(n >= 0, "negative size");
   CK_REQUIRE(info, "info is NULL");
@@ -422,27 +479,55 @@ extern "C" int ck_potrf(double* a, ck_i64 n, ck_i64 ld, void* ws, int* info, voi
   if (n == 0) return CK_OK;
   CK_REQUIRE(a && ws, "null pointer");
   CK_REQUIRE(ld >= n, "ld (%lld) < n (%lld)", (long long)ld, (long long)n);
-  double* xinv = static_cast<double*>(ws);
+  CholCtx c{a, n, ld, static_cast<double*>(ws), info, st};
+  const ck_i64 nblk = (n + CK_NB - 1) / CK_NB;
+  const int agg = agg_blocks();
   int rc;
-  for (ck_i64 k0 = 0, kb = 0; k0 < n; k0 += CK_NB, ++kb) {
-    const int nb = (int)((n - k0 < CK_NB) ? n - k0 : CK_NB);
-    const ck_i64 k1 = k0 + nb;
-    double* xk = xinv + kb * CK_NB * CK_NB;
-    if ((rc = potf2_launch(a + k0 * ld + k0, ld, nb, xk, info, (int)k0, st))) return rc;
+  for (ck_i64 b0 = 0; b0 < nblk; b0 += agg) {
+    const ck_i64 b1 = b0 + agg < nblk ? b0 + agg : nblk;
+    if ((rc = factor_range(c, b0, b1))) return rc;
+    const ck_i64 k0 = c.s(b0), k1 = c.s(b1);
     if (k1 < n) {
-      GemmArgs t;  // panel: A[k1:, k0:k1] <- A[k1:, k0:k1] X_k^T   (in place, one column tile)
-      t.A = a + k1 * ld + k0; t.lda = ld;
-      t.B = xk; t.ldb = CK_NB;
-      t.C = a + k1 * ld + k0; t.ldc = ld;
-      t.M = n - k1; t.N = nb; t.K = nb; t.mode = 0; t.lower_only = 0;
-      if ((rc = gemm_launch<2, 4>(t, st))) return rc;
-      GemmArgs s;  // trailing: A[k1:, k1:] -= P P^T, lower tiles
+      GemmArgs s;  // trailing: A[k1:, k1:] -= P P^T with P = A[k1:, k0:k1], lower tiles, K = 128 * agg
       s.A = a + k1 * ld + k0; s.lda = ld;
       s.B = a + k1 * ld + k0; s.ldb = ld;
       s.C = a + k1 * ld + k1; s.ldc = ld;
-      s.M = n - k1; s.N = n - k1; s.K = nb; s.mode = 1; s.lower_only = 1;
+      s.M = n - k1; s.N = n - k1; s.K = k1 - k0; s.mode = 1; s.lower_only = 1;
       if ((rc = gemm_launch<4, 2>(s, st))) return rc;
     }
+  }
+  return CK_OK;
+}
+
+struct TrsmCtx {
+  const double* l; ck_i64 n, ld; const double* xinv; double* rhs; ck_i64 nrhs, ldr; cudaStream_t st;
+  ck_i64 s(ck_i64 b) const { return b * CK_NB < n ? b * CK_NB : n; }
+};
+
+// forward substitution restricted to the column blocks [b0, b1) of the target-major right-hand sides
+static int solve_range(const TrsmCtx& c, ck_i64 b0, ck_i64 b1) {
+  int rc;
+  if (b1 - b0 == 1) {
+    const ck_i64 k0 = c.s(b0);
+    const int nb = (int)(c.s(b1) - k0);
+    GemmArgs t;  // V[:, k] = R[:, k] X_k^T  (in place)
+    t.A = c.rhs + k0; t.lda = c.ldr;
+    t.B = c.xinv + b0 * CK_NB * CK_NB; t.ldb = CK_NB;
+    t.C = c.rhs + k0; t.ldc = c.ldr;
+    t.M = c.nrhs; t.N = nb; t.K = nb; t.mode = 0; t.lower_only = 0;
+    return gemm_launch<2, 4>(t, c.st);
+  }
+  const ck_i64 mid = b0 + (b1 - b0 + 1) / 2;
+  if ((rc = solve_range(c, b0, mid))) return rc;
+  const ck_i64 r0 = c.s(mid), cl = c.s(b0), ce = c.s(b1);
+  if (r0 < c.n) {
+    GemmArgs u;  // R[:, r0:ce] -= V[:, cl:r0] L[r0:ce, cl:r0]^T
+    u.A = c.rhs + cl; u.lda = c.ldr;
+    u.B = c.l + r0 * c.ld + cl; u.ldb = c.ld;
+    u.C = c.rhs + r0; u.ldc = c.ldr;
+    u.M = c.nrhs; u.N = ce - r0; u.K = r0 - cl; u.mode = 1; u.lower_only = 0;
+    if ((rc = gemm_launch<4, 2>(u, c.st))) return rc;
+    if ((rc = solve_range(c, mid, b1))) return rc;
   }
   return CK_OK;
 }
@@ -453,25 +538,21 @@ extern "C" int ck_trsm_lower(const double* l, ck_i64 n, ck_i64 ld, const void* w
   if (n == 0 || nrhs == 0) return CK_OK;
   CK_REQUIRE(l && ws && rhs, "null pointer");
   CK_REQUIRE(ld >= n && ld_rhs >= n, "leading dimension too small");
-  cudaStream_t st = ck_stream(stream);
-  const double* xinv = static_cast<const double*>(ws);
+  TrsmCtx c{l, n, ld, static_cast<const double*>(ws), rhs, nrhs, ld_rhs, ck_stream(stream)};
+  const ck_i64 nblk = (n + CK_NB - 1) / CK_NB;
+  const int agg = agg_blocks();
   int rc;
-  for (ck_i64 k0 = 0, kb = 0; k0 < n; k0 += CK_NB, ++kb) {
-    const int nb = (int)((n - k0 < CK_NB) ? n - k0 : CK_NB);
-    const ck_i64 k1 = k0 + nb;
-    GemmArgs t;  // V[:, k] = R[:, k] X_k^T  (in place)
-    t.A = rhs + k0; t.lda = ld_rhs;
-    t.B = xinv + kb * CK_NB * CK_NB; t.ldb = CK_NB;
-    t.C = rhs + k0; t.ldc = ld_rhs;
-    t.M = nrhs; t.N = nb; t.K = nb; t.mode = 0; t.lower_only = 0;
-    if ((rc = gemm_launch<2, 4>(t, st))) return rc;
+  for (ck_i64 b0 = 0; b0 < nblk; b0 += agg) {
+    const ck_i64 b1 = b0 + agg < nblk ? b0 + agg : nblk;
+    if ((rc = solve_range(c, b0, b1))) return rc;
+    const ck_i64 k0 = c.s(b0), k1 = c.s(b1);
     if (k1 < n) {
-      GemmArgs u;  // R[:, k1:] -= V[:, k] L[k1:, k]^T
+      GemmArgs u;  // R[:, k1:] -= V[:, k0:k1] L[k1:, k0:k1]^T, K = 128 * agg
       u.A = rhs + k0; u.lda = ld_rhs;
       u.B = l + k1 * ld + k0; u.ldb = ld;
       u.C = rhs + k1; u.ldc = ld_rhs;
-      u.M = nrhs; u.N = n - k1; u.K = nb; u.mode = 1; u.lower_only = 0;
-      if ((rc = gemm_launch<4, 2>(u, st))) return rc;
+      u.M = nrhs; u.N = n - k1; u.K = k1 - k0; u.mode = 1; u.lower_only = 0;
+      if ((rc = gemm_launch<4, 2>(u, c.st))) return rc;
     }
   }
   return CK_OK;
