@@ -144,19 +144,30 @@ int ck_nll(const double* xy0_dev, ck_i64 n0, const double* xy1_dev, ck_i64 n1, c
 
 size_t ck_vario_minmax_workspace_bytes(ck_i64 na, ck_i64 nb);
 
+/* Pair tiles.  All K2 passes visit the pairs in tiles of (tile_rows x tile_cols) points of (A x B); the
+ * tile decomposition depends only on (na, nb).  Every pass takes a tile-ROW range
+ * [tile_row_begin, tile_row_end): (0, -1) = all rows (single GPU); on several GPUs each rank passes its
+ * share of the rows of A (row-block partition, cokrig_b200/parallel.py) and the per-tile partials are
+ * combined afterwards, so results do not depend on the number of ranks. */
+ck_i64 ck_vario_tile_rows(ck_i64 na);
+ck_i64 ck_vario_tile_cols(ck_i64 nb);
+int ck_vario_tile_shape(int* rows_per_tile /*HOST*/, int* cols_per_tile /*HOST*/);
+
 /* Pass 1: over all pairs (a < b if same_field, else all a, b) with d <= max_dist (+ guard band):
  *   out_dev[0] = min{d : d > 0} (+inf if none), out_dev[1] = max d (-inf if none),
  *   out_dev[2] = number of such pairs (as double, exact below 2^53);  ws_dev keeps per-tile extrema.
  * Replaces the two reductions of fields._construct_variogram_bins (src/fields.py:394-395). */
 int ck_vario_minmax(const double* xya_dev, ck_i64 na, const double* xyb_dev, ck_i64 nb, int metric, int same_field,
-                    double max_dist, double* out_dev, void* ws_dev, void* stream);
+                    double max_dist, ck_i64 tile_row_begin, ck_i64 tile_row_end, double* out_dev, void* ws_dev,
+                    void* stream);
 
 /* Index pairs (a, b) with 0 < d <= lo or d >= hi (and d <= max_dist + guard): the candidates for the
  * exact extrema.  pairs_dev holds 2*capacity entries; *count_dev may exceed capacity (then only the
  * first `capacity` pairs were stored).  ws_dev is the workspace filled by ck_vario_minmax. */
 int ck_vario_candidates(const double* xya_dev, ck_i64 na, const double* xyb_dev, ck_i64 nb, int metric, int same_field,
-                        double max_dist, double lo, double hi, const void* ws_dev, ck_i64* pairs_dev, ck_i64 capacity,
-                        unsigned long long* count_dev, void* stream);
+                        double max_dist, double lo, double hi, ck_i64 tile_row_begin, ck_i64 tile_row_end,
+                        const void* ws_dev, ck_i64* pairs_dev, ck_i64 capacity, unsigned long long* count_dev,
+                        void* stream);
 
 size_t ck_vario_bin_workspace_bytes(ck_i64 na, ck_i64 nb, int n_bins);
 
@@ -173,6 +184,22 @@ int ck_vario_bin(const double* xya_dev, const double* va_dev, ck_i64 na, double 
                  double max_dist, const double* edges /*HOST*/, int n_bins, unsigned long long* counts_dev,
                  double* sums_dev, ck_i64* flagged_dev, ck_i64 flag_capacity, unsigned long long* flag_count_dev,
                  void* ws_dev, void* stream);
+
+/* The two stages of ck_vario_bin, for the row-block multi-GPU partition: _tiles fills the per-tile
+ * partials of tile rows [tile_row_begin, tile_row_end) inside ws_dev (all other partials are set to
+ * zero); the ranks then sum their partial arrays (each entry has exactly one non-zero contributor, so the
+ * sum is exact and order-free) and _reduce combines the tiles in the fixed order of the single-GPU path:
+ * counts and sums are bit-identical for any number of ranks.  The partial arrays start
+ * ck_vario_bin_partials_offset(n_bins) bytes into ws_dev: tiles*n_bins doubles, then (256-byte aligned)
+ * tiles*n_bins uint32, tiles = ck_vario_tile_rows(na) * ck_vario_tile_cols(nb). */
+size_t ck_vario_bin_partials_offset(int n_bins);
+int ck_vario_bin_tiles(const double* xya_dev, const double* va_dev, ck_i64 na, double mean_a, const double* xyb_dev,
+                       const double* vb_dev, ck_i64 nb, double mean_b, int metric, int same_field, int covariogram,
+                       double max_dist, const double* edges /*HOST*/, int n_bins, ck_i64 tile_row_begin,
+                       ck_i64 tile_row_end, ck_i64* flagged_dev, ck_i64 flag_capacity, unsigned long long* flag_count_dev,
+                       void* ws_dev, void* stream);
+int ck_vario_bin_reduce(ck_i64 na, ck_i64 nb, int n_bins, const void* ws_dev, unsigned long long* counts_dev,
+                        double* sums_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K4  batched local-neighbourhood cokriging (point prediction)
@@ -193,6 +220,43 @@ int ck_local_predict(const double* xy0_dev, const double* z0_dev, ck_i64 n0, con
                      ck_i64 n1, const double* xyp_dev, ck_i64 m, const double* params /*HOST*/, int n_procs, int i_pred,
                      int metric, double max_dist, int cv, const int* k_dev, ck_i64 kmax, double* pred_dev,
                      double* sd_dev, int* info_dev, void* ws_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Multi-GPU building blocks (one process per GPU; the collectives are NCCL broadcasts issued by the host
+ * side, cokrig_b200/parallel.py).  The large system is the AUGMENTED array
+ *     [ Sigma (N x N, lower tiles) ; C^T (targets x N) + z ]      square tiles of `tb` elements,
+ * 2-D block-cyclic over a P x Q process grid: tile (I, J) on rank (I mod P, J mod Q), local tile
+ * (I div P, J div Q).  One right-looking Cholesky sweep over the tile columns applied to all rows
+ * leaves L, V = L^-1 c and y = L^-1 z (src/joint_prediction.py:68-73 without a second pass over L).
+ * No counterpart in the reference (single process); SURVEY 8(e).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Number of tiles t in [0, ntiles) with t mod nprocs == rank. */
+ck_i64 ck_mg_local_tiles(ck_i64 ntiles, ck_i64 nprocs, ck_i64 rank);
+
+/* Assemble this rank's tiles of the augmented array from the replicated coordinates (K1 per tile).
+ * Row tiles 0 .. TC-1 (TC = ceil(N/tb)) hold Sigma (tiles with J <= I only; the pad beyond N is the
+ * identity); row tiles TC + e hold tb-1 targets each (rows of ck_cross_cov) and z in their last row.
+ * local_dev: (local row tiles * tb) x ld, ld >= local column tiles * tb. */
+int ck_mg_assemble(const double* xy0_dev, ck_i64 n0, const double* xy1_dev, ck_i64 n1, const double* xyp_dev, ck_i64 m,
+                   const double* z_dev, const double* params /*HOST*/, int n_procs, int i_pred, int metric, ck_i64 tb,
+                   int P, int p, int Q, int q, double* local_dev, ck_i64 ld, void* stream);
+
+/* C = A B^T (subtract == 0) or C -= A B^T: A (m x k), B (n x k), C (m x n), row-major, FP64 DMMA. */
+int ck_gemm_nt(const double* a_dev, ck_i64 lda, const double* b_dev, ck_i64 ldb, double* c_dev, ck_i64 ldc, ck_i64 m,
+               ck_i64 n, ck_i64 k, int subtract, void* stream);
+
+/* Trailing update of the local part of the block-cyclic array: C -= A B^T on the local tiles whose
+ * global indices satisfy J <= I (J == I: lower triangle of the tile only).  Local tile (li, lj) of C is
+ * global tile (row_tile0 + li * row_tile_step, col_tile0 + lj * col_tile_step); m, n whole tiles. */
+int ck_mg_update(const double* a_dev, ck_i64 lda, const double* b_dev, ck_i64 ldb, double* c_dev, ck_i64 ldc, ck_i64 m,
+                 ck_i64 n, ck_i64 k, ck_i64 tb, ck_i64 row_tile0, ck_i64 row_tile_step, ck_i64 col_tile0,
+                 ck_i64 col_tile_step, void* stream);
+
+/* Row-wise partial sums over the local columns: out_vy[r] = v_r . y_r, out_vv[r] = |v_r|^2 with
+ * v_r = v + r*ldv, y_r = y + r*ldy (ldy = 0: one shared y), fixed summation order. */
+int ck_row_dots(const double* v_dev, ck_i64 ldv, ck_i64 nrows, ck_i64 ncols, const double* y_dev, ck_i64 ldy,
+                double* out_vy_dev, double* out_vv_dev, void* stream);
 
 #ifdef __cplusplus
 }

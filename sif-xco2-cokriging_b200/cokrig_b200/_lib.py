@@ -58,9 +58,23 @@ SIGNATURES = {
     "ck_nll": (c_int, [_dp, c_int64, _dp, c_int64, _hp, c_int, c_int, _dp, _dp, c_int64, _dp, _dp, _dp, _dp,
                        c_void_p]),
     "ck_vario_minmax_workspace_bytes": (c_size_t, [c_int64, c_int64]),
-    "ck_vario_minmax": (c_int, [_dp, c_int64, _dp, c_int64, c_int, c_int, c_double, _dp, _dp, c_void_p]),
-    "ck_vario_candidates": (c_int, [_dp, c_int64, _dp, c_int64, c_int, c_int, c_double, c_double, c_double, _dp, _dp,
-                                    c_int64, _dp, c_void_p]),
+    "ck_vario_tile_rows": (c_int64, [c_int64]),
+    "ck_vario_tile_cols": (c_int64, [c_int64]),
+    "ck_vario_tile_shape": (c_int, [POINTER(c_int), POINTER(c_int)]),
+    "ck_vario_minmax": (c_int, [_dp, c_int64, _dp, c_int64, c_int, c_int, c_double, c_int64, c_int64, _dp, _dp, c_void_p]),
+    "ck_vario_candidates": (c_int, [_dp, c_int64, _dp, c_int64, c_int, c_int, c_double, c_double, c_double, c_int64,
+                                    c_int64, _dp, _dp, c_int64, _dp, c_void_p]),
+    "ck_vario_bin_partials_offset": (c_size_t, [c_int]),
+    "ck_vario_bin_tiles": (c_int, [_dp, _dp, c_int64, c_double, _dp, _dp, c_int64, c_double, c_int, c_int, c_int,
+                                   c_double, _hp, c_int, c_int64, c_int64, _dp, c_int64, _dp, _dp, c_void_p]),
+    "ck_vario_bin_reduce": (c_int, [c_int64, c_int64, c_int, _dp, _dp, _dp, c_void_p]),
+    "ck_mg_local_tiles": (c_int64, [c_int64, c_int64, c_int64]),
+    "ck_mg_assemble": (c_int, [_dp, c_int64, _dp, c_int64, _dp, c_int64, _dp, _hp, c_int, c_int, c_int, c_int64,
+                               c_int, c_int, c_int, c_int, _dp, c_int64, c_void_p]),
+    "ck_gemm_nt": (c_int, [_dp, c_int64, _dp, c_int64, _dp, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p]),
+    "ck_mg_update": (c_int, [_dp, c_int64, _dp, c_int64, _dp, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
+                             c_int64, c_int64, c_int64, c_void_p]),
+    "ck_row_dots": (c_int, [_dp, c_int64, c_int64, c_int64, _dp, c_int64, _dp, _dp, c_void_p]),
     "ck_vario_bin_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int]),
     "ck_vario_bin": (c_int, [_dp, _dp, c_int64, c_double, _dp, _dp, c_int64, c_double, c_int, c_int, c_int,
                              c_double, _hp, c_int, _dp, _dp, _dp, c_int64, _dp, _dp, c_void_p]),

@@ -241,24 +241,31 @@ def _read_pairs(pairs: torch.Tensor, count: torch.Tensor, what: str):
     return pairs[:n].cpu().numpy()
 
 
-def vario_extrema(Xa: torch.Tensor, Xb: torch.Tensor, metric: int, same_field: bool, max_dist: float) -> dict:
+def vario_extrema(Xa: torch.Tensor, Xb: torch.Tensor, metric: int, same_field: bool, max_dist: float,
+                  tile_rows=(0, -1), combine=None) -> dict:
     """Device pass 1: {'min': min non-zero distance, 'max': max distance, 'count': pairs} over pairs
     with d <= max_dist, plus 'candidates': (a, b) index pairs inside the guard band of the extrema
-    (haversine only; None for the exact Euclidean metric)."""
+    (haversine only; None for the exact Euclidean metric).
+
+    tile_rows: this rank's share of the pair-tile rows ((0, -1) = all).  combine: callable that maps the
+    local (min, max, count) to the global one (MIN / MAX / SUM across ranks, parallel.py); the candidate
+    list is then this rank's part of the global guard band."""
     na, nb = Xa.shape[0], Xb.shape[0]
     out = torch.empty(3, dtype=F64, device=Xa.device)
     ws = torch.empty(int(lib.ck_vario_minmax_workspace_bytes(na, nb)) // 8 + 1, dtype=F64, device=Xa.device)
-    check(lib.ck_vario_minmax(_ptr(Xa), na, _ptr(Xb), nb, metric, int(same_field), float(max_dist), _ptr(out), _ptr(ws),
-                              _stream()), "ck_vario_minmax")
+    check(lib.ck_vario_minmax(_ptr(Xa), na, _ptr(Xb), nb, metric, int(same_field), float(max_dist), tile_rows[0],
+                              tile_rows[1], _ptr(out), _ptr(ws), _stream()), "ck_vario_minmax")
     mn, mx, cnt = out.cpu().tolist()
+    if combine is not None:
+        mn, mx, cnt = combine(mn, mx, cnt)
     res = {"min": mn, "max": mx, "count": int(cnt), "candidates": None}
     if metric == METRIC_HAVERSINE and cnt > 0:
         pairs = torch.empty((VARIO_LIST_CAPACITY, 2), dtype=torch.int64, device=Xa.device)
         count = torch.zeros(1, dtype=torch.int64, device=Xa.device)
         lo, hi = mn * (1.0 + 2 * VARIO_GUARD), mx * (1.0 - 2 * VARIO_GUARD)
         check(lib.ck_vario_candidates(_ptr(Xa), na, _ptr(Xb), nb, metric, int(same_field), float(max_dist), lo, hi,
-                                      _ptr(ws), _ptr(pairs), VARIO_LIST_CAPACITY, _ptr(count), _stream()),
-              "ck_vario_candidates")
+                                      tile_rows[0], tile_rows[1], _ptr(ws), _ptr(pairs), VARIO_LIST_CAPACITY, _ptr(count),
+                                      _stream()), "ck_vario_candidates")
         res["candidates"] = _read_pairs(pairs, count, "variogram extrema")
     return res
 
@@ -269,23 +276,40 @@ def vario_minmax(Xa: torch.Tensor, Xb: torch.Tensor, metric: int, same_field: bo
 
 
 def vario_bin(Xa: torch.Tensor, va: torch.Tensor, mean_a: float, Xb: torch.Tensor, vb: torch.Tensor, mean_b: float,
-              metric: int, same_field: bool, covariogram: bool, max_dist: float, edges: np.ndarray, guard: bool = True):
+              metric: int, same_field: bool, covariogram: bool, max_dist: float, edges: np.ndarray, guard: bool = True,
+              tile_rows=(0, -1), combine=None):
     """Device pass 2: per-bin (counts int64, sums float64, flagged) with pandas.cut(include_lowest=True)
-    semantics; `flagged` = (a, b) index pairs left undecided inside the guard band (or None)."""
+    semantics; `flagged` = (a, b) index pairs left undecided inside the guard band (or None).
+
+    tile_rows / combine: row-block multi-GPU partition.  Every rank bins its own pair-tile rows into the
+    per-tile partial arrays (zeros elsewhere); `combine(sums_partials, counts_partials)` sums them across
+    ranks in place (exact: one non-zero contributor per entry) and the fixed-order tile reduction then
+    gives counts and sums that are bit-identical for any number of ranks."""
     e = np.ascontiguousarray(np.asarray(edges, dtype=np.float64))
     n_bins = e.size - 1
     na, nb = Xa.shape[0], Xb.shape[0]
-    ws = torch.empty(int(lib.ck_vario_bin_workspace_bytes(na, nb, n_bins)) // 8 + 1, dtype=F64, device=Xa.device)
-    counts = torch.empty(n_bins, dtype=torch.int64, device=Xa.device)
-    sums = torch.empty(n_bins, dtype=F64, device=Xa.device)
+    counts = torch.zeros(n_bins, dtype=torch.int64, device=Xa.device)
+    sums = torch.zeros(n_bins, dtype=F64, device=Xa.device)
     use_guard = guard and metric == METRIC_HAVERSINE
+    if na == 0 or nb == 0:
+        return counts.cpu().numpy(), sums.cpu().numpy(), (np.empty((0, 2), dtype=np.int64) if use_guard else None)
+    nbytes = int(lib.ck_vario_bin_workspace_bytes(na, nb, n_bins))
+    ws = torch.empty(nbytes // 8 + 1, dtype=F64, device=Xa.device)
     pairs = torch.empty((VARIO_LIST_CAPACITY, 2), dtype=torch.int64, device=Xa.device) if use_guard else None
     count = torch.zeros(1, dtype=torch.int64, device=Xa.device)
-    check(lib.ck_vario_bin(_ptr(Xa), _ptr(va), na, float(mean_a), _ptr(Xb), _ptr(vb), nb, float(mean_b), metric,
-                           int(same_field), int(covariogram), float(max_dist),
-                           e.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), n_bins, _ptr(counts), _ptr(sums),
-                           _ptr(pairs), VARIO_LIST_CAPACITY if use_guard else 0, _ptr(count), _ptr(ws), _stream()),
-          "ck_vario_bin")
+    check(lib.ck_vario_bin_tiles(_ptr(Xa), _ptr(va), na, float(mean_a), _ptr(Xb), _ptr(vb), nb, float(mean_b), metric,
+                                 int(same_field), int(covariogram), float(max_dist),
+                                 e.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), n_bins, tile_rows[0], tile_rows[1],
+                                 _ptr(pairs), VARIO_LIST_CAPACITY if use_guard else 0, _ptr(count), _ptr(ws), _stream()),
+          "ck_vario_bin_tiles")
+    if combine is not None:
+        tiles = int(lib.ck_vario_tile_rows(na)) * int(lib.ck_vario_tile_cols(nb))
+        off = int(lib.ck_vario_bin_partials_offset(n_bins)) // 8
+        psum = ws[off: off + tiles * n_bins]
+        off_c = off + ((tiles * n_bins * 8 + 255) // 256 * 256) // 8
+        pcnt = ws[off_c: off_c + (tiles * n_bins * 4 + 7) // 8].view(torch.int32)[: tiles * n_bins]
+        combine(psum, pcnt)
+    check(lib.ck_vario_bin_reduce(na, nb, n_bins, _ptr(ws), _ptr(counts), _ptr(sums), _stream()), "ck_vario_bin_reduce")
     flagged = _read_pairs(pairs, count, "variogram binning") if use_guard else None
     return counts.cpu().numpy(), sums.cpu().numpy(), flagged
 

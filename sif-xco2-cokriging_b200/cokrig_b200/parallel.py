@@ -1,0 +1,459 @@
+"""Multi-GPU partitioning of the cokriging hot path: one process per GPU, torch.distributed (NCCL over
+NVLink / NVSwitch) for the plumbing, the hand-written kernels of libcokrig_b200.so for every local step.
+
+The reference is single-process (its only parallelism is a multiprocessing.Pool over prediction
+targets, src/point_prediction.py:69-81); this module is where the path shards naturally:
+
+  VarioShard             K2: pair tiles row-block partitioned over ranks; per-tile partials combined by an
+                         exact sum, then the single-GPU fixed-order tile reduction -> counts AND sums are
+                         bit-identical for any number of ranks.
+  shard_windows          C4: independent weekly windows round-robin over ranks (no data-path collective).
+  fd_gradient            C3: the P+1 objective evaluations of one finite-difference gradient, one theta per rank.
+  BlockCyclicCokriging   C5: the large joint system as ONE augmented array [Sigma ; C^T + z], square tiles,
+                         2-D block-cyclic over a P x Q grid; right-looking tile Cholesky with NCCL panel
+                         broadcasts and one-panel look-ahead; factor and solve in a single sweep.
+
+Every compute step goes through a small "kernel set" object.  The product kernel set is CudaKernels
+(ctypes -> libcokrig_b200.so; raises without a CUDA device -- there is no CPU fallback).  The CPU test
+tier (gloo, world_size 2) injects a numpy kernel set that lives under tests/ to exercise the
+partitioning, communication order and reductions without a GPU.
+"""
+from __future__ import annotations
+
+import contextlib
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+F64 = torch.float64
+
+
+# ------------------------------------------------------------------------------------------------ grid
+def grid_shape(world: int) -> Tuple[int, int]:
+    """P x Q process grid for `world` ranks: as square as possible with P <= Q (8 -> 2 x 4)."""
+    p = int(np.floor(np.sqrt(world)))
+    while world % p:
+        p -= 1
+    return p, world // p
+
+
+class ProcessGrid:
+    """rank = p * Q + q.  Column groups (fixed q) carry the diagonal-tile broadcast; panel broadcasts use
+    the world group."""
+
+    def __init__(self, P: Optional[int] = None, Q: Optional[int] = None):
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        if P is None or Q is None:
+            P, Q = grid_shape(self.world)
+        if P * Q != self.world:
+            raise ValueError(f"process grid {P}x{Q} does not match world size {self.world}")
+        self.P, self.Q = P, Q
+        self.p, self.q = divmod(self.rank, Q)
+        self.col_groups = [None] * Q
+        if self.world > 1 and P > 1:
+            for qq in range(Q):  # every rank must create every group, in the same order
+                self.col_groups[qq] = dist.new_group([pp * Q + qq for pp in range(P)])
+
+    def rank_of(self, p: int, q: int) -> int:
+        return p * self.Q + q
+
+
+def local_tiles(ntiles: int, nprocs: int, rank: int) -> int:
+    """Number of tiles t in [0, ntiles) with t % nprocs == rank (== ck_mg_local_tiles)."""
+    return 0 if ntiles <= rank else (ntiles - rank + nprocs - 1) // nprocs
+
+
+def first_local_after(k: int, nprocs: int, rank: int) -> int:
+    """Smallest local tile index l with global index l * nprocs + rank > k."""
+    return (k - rank) // nprocs + 1 if k >= rank else 0
+
+
+# ------------------------------------------------------------------------------------------------ C4 / C3
+def shard_windows(n_windows: int, rank: int, world: int) -> List[int]:
+    """Independent systems (weekly windows, BASELINE config 4) handled by `rank`: round-robin."""
+    return list(range(rank, n_windows, world))
+
+
+def gather_window_results(local: dict, n_windows: int) -> Optional[list]:
+    """Collect {window index: result} from all ranks on rank 0, in window order."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return [local[w] for w in range(n_windows)]
+    parts = [None] * dist.get_world_size() if dist.get_rank() == 0 else None
+    dist.gather_object(local, parts, dst=0)
+    if dist.get_rank() != 0:
+        return None
+    merged = {}
+    for part in parts:
+        merged.update(part)
+    return [merged[w] for w in range(n_windows)]
+
+
+def fd_gradient(objective: Callable[[np.ndarray], float], theta: np.ndarray, eps: float = 1.4901161193847656e-08,
+                device=None) -> Tuple[float, np.ndarray]:
+    """Objective value and 2-point forward-difference gradient (what scipy's L-BFGS-B does for the
+    reference fit, src/model.py:306-312) with the P+1 evaluations dealt round-robin to the ranks; every
+    rank returns the same (f, grad).  Evaluation j=0 is theta itself, j>0 perturbs parameter j-1."""
+    theta = np.asarray(theta, dtype=np.float64)
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    vals = torch.zeros(theta.size + 1, dtype=F64, device=device)
+    for j in range(rank, theta.size + 1, world):
+        t = theta.copy()
+        if j > 0:
+            t[j - 1] += eps
+        vals[j] = float(objective(t))
+    if world > 1:
+        dist.all_reduce(vals)  # every slot has exactly one non-zero contributor: exact
+    v = vals.cpu().numpy()
+    return float(v[0]), (v[1:] - v[0]) / eps
+
+
+# ------------------------------------------------------------------------------------------------ K2
+class VarioShard:
+    """Row-block partition of the K2 pair tiles.  `tile_rows(...)` gives this rank's share of
+    the tile rows of A, balanced by pair count (for a marginal variogram only tiles above the diagonal do
+    work, so the split is triangular); the combine_* callables plug into ops.vario_extrema / vario_bin."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    @staticmethod
+    def split(ta: int, tb: int, va: int, vb: int, same_field: bool, world: int) -> List[int]:
+        """Boundaries b[0..world] over the `ta` tile rows with ~equal numbers of active tiles."""
+        if same_field:  # tile (i, j) is active unless b0 + vb - 1 <= a0  <=>  (j + 1) * vb - 1 > i * va
+            w = np.array([tb - min(tb, (i * va + 1) // vb) for i in range(ta)], dtype=np.float64)
+        else:
+            w = np.full(ta, float(tb))
+        c = np.concatenate([[0.0], np.cumsum(w)])
+        bounds = [int(np.searchsorted(c, c[-1] * r / world, side="left")) for r in range(world + 1)]
+        bounds[0], bounds[-1] = 0, ta
+        for r in range(1, world + 1):
+            bounds[r] = max(bounds[r], bounds[r - 1])
+        return bounds
+
+    def tile_rows(self, ta: int, tb: int, va: int, vb: int, same_field: bool) -> Tuple[int, int]:
+        b = self.split(ta, tb, va, vb, same_field, self.world)
+        return b[self.rank], b[self.rank + 1]
+
+    def combine_extrema(self, mn: float, mx: float, cnt: float, device=None):
+        if self.world == 1:
+            return mn, mx, cnt
+        t = torch.tensor([mn, -mx], dtype=F64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+        c = torch.tensor([cnt], dtype=F64, device=device)
+        dist.all_reduce(c, group=self.group)
+        return float(t[0]), float(-t[1]), float(c[0])
+
+    def combine_partials(self, psum: torch.Tensor, pcnt: torch.Tensor) -> None:
+        if self.world == 1:
+            return
+        dist.all_reduce(psum, group=self.group)  # one non-zero contributor per entry -> exact
+        dist.all_reduce(pcnt, group=self.group)
+
+    def gather_pairs(self, pairs: Optional[np.ndarray]) -> Optional[np.ndarray]:
+        """Union of the guard-band index pairs found by every rank (identical on all ranks, rank order)."""
+        if pairs is None or self.world == 1:
+            return pairs
+        parts = [None] * self.world
+        dist.all_gather_object(parts, np.asarray(pairs, dtype=np.int64).reshape(-1, 2), group=self.group)
+        return np.concatenate(parts, axis=0)
+
+
+# ------------------------------------------------------------------------------------------------ C5
+class CudaKernels:
+    """The product kernel set: every method is one or a few C-ABI calls on CUDA tensors."""
+
+    def __init__(self, device=None):
+        from . import ops
+        from ._lib import check, lib
+        self.ops, self.lib, self.check = ops, lib, check
+        self.device = ops.require_cuda() if device is None else torch.device(device)
+        lo, hi = torch.cuda.Stream.priority_range()
+        self.main = torch.cuda.current_stream(self.device)
+        self.panel = torch.cuda.Stream(self.device, priority=hi)
+
+    # memory / ordering ------------------------------------------------------------------------
+    def empty(self, *shape, dtype=F64):
+        return torch.empty(*shape, dtype=dtype, device=self.device)
+
+    def zeros(self, *shape, dtype=F64):
+        return torch.zeros(*shape, dtype=dtype, device=self.device)
+
+    def to_device(self, a):
+        return self.ops.to_device(a)
+
+    def stream(self, which: str):
+        return torch.cuda.stream(self.panel if which == "panel" else self.main)
+
+    def event(self):
+        e = torch.cuda.Event()
+        e.record()
+        return e
+
+    def wait(self, event) -> None:
+        if event is not None:
+            torch.cuda.current_stream(self.device).wait_event(event)
+
+    def sync(self) -> None:
+        torch.cuda.synchronize(self.device)
+
+    # compute -----------------------------------------------------------------------------------
+    def pack_size(self, tb: int) -> int:
+        return tb * tb + int(self.lib.ck_potrf_workspace_bytes(tb)) // 8
+
+    def assemble(self, coords, targets, z, params, n_procs, i_pred, metric, tb, grid: ProcessGrid, local):
+        o = self.ops
+        _, pp = o._params(params, n_procs)
+        c1 = coords[1] if n_procs == 2 else None
+        n1 = coords[1].shape[0] if n_procs == 2 else 0
+        self.check(self.lib.ck_mg_assemble(o._ptr(coords[0]), coords[0].shape[0], o._ptr(c1), n1, o._ptr(targets),
+                                           targets.shape[0], o._ptr(z), pp, n_procs, i_pred, metric, tb, grid.P, grid.p,
+                                           grid.Q, grid.q, o._ptr(local), local.stride(0), o._stream()), "ck_mg_assemble")
+
+    def potrf_tile(self, tile: torch.Tensor, pack: torch.Tensor, info: torch.Tensor) -> None:
+        """In-place Cholesky of the (tb x tb) view `tile`; pack <- [L tile (dense tb x tb) | inverted diagonal blocks]."""
+        o, tb = self.ops, tile.shape[0]
+        self.check(self.lib.ck_potrf(o._ptr(tile), tb, tile.stride(0), o._ptr(pack[tb * tb:]), o._ptr(info), o._stream()),
+                   "ck_potrf")
+        pack[: tb * tb].view(tb, tb).copy_(tile)
+
+    def trsm(self, pack: torch.Tensor, tb: int, rows: torch.Tensor) -> None:
+        """rows <- rows L^-T for the (nrows x tb) view `rows` (row stride = its leading dimension)."""
+        o = self.ops
+        self.check(self.lib.ck_trsm_lower(o._ptr(pack), tb, tb, o._ptr(pack[tb * tb:]), o._ptr(rows), rows.shape[0],
+                                          rows.stride(0), o._stream()), "ck_trsm_lower")
+
+    def update(self, A, B, C, tb, gi0, gis, gj0, gjs) -> None:
+        o = self.ops
+        self.check(self.lib.ck_mg_update(o._ptr(A), A.stride(0), o._ptr(B), B.stride(0), o._ptr(C), C.stride(0), C.shape[0],
+                                         C.shape[1], A.shape[1], tb, gi0, gis, gj0, gjs, o._stream()), "ck_mg_update")
+
+    def row_dots(self, V: torch.Tensor, y: torch.Tensor):
+        o = self.ops
+        vy, vv = self.empty(V.shape[0]), self.empty(V.shape[0])
+        self.check(self.lib.ck_row_dots(o._ptr(V), V.stride(0), V.shape[0], V.shape[1], o._ptr(y), 0, o._ptr(vy), o._ptr(vv),
+                                        o._stream()), "ck_row_dots")
+        return vy, vv
+
+
+class BlockCyclicCokriging:
+    """Joint simple cokriging (src/joint_prediction.py:50-78) of one large system on a P x Q grid of GPUs.
+
+    Layout: see csrc/ck_mg.cu.  Per tile column k (right-looking):
+        diagonal owner      potrf(tile k,k)                                  -> broadcast down process column k%Q
+        process column k%Q  panel rows I>k:  A_Ik <- A_Ik L_kk^-T (TRSM)     -> broadcast to every rank
+        every rank          A_IJ -= L_Ik L_Jk^T on its tiles I>k, J>k, J<=I  (one DMMA launch, ck_mg_update)
+    with one-panel look-ahead: the owners of column k+1 update that column first, factor it and start its
+    broadcasts on a high-priority stream while everybody's trailing update of step k is still running.
+    The target rows (C^T and z) ride along as extra row tiles, so after the sweep they hold L^-1 c and
+    L^-1 z:  pred = (L^-1 c).(L^-1 z),  var = c0 - |L^-1 c|^2, reduced over the process row in rank order.
+    """
+
+    def __init__(self, grid: ProcessGrid, tile: int = 1024, kernels=None, lookahead: bool = True):
+        if tile % 128:
+            raise ValueError("tile must be a multiple of 128")
+        self.g, self.tb = grid, int(tile)
+        self.k = kernels if kernels is not None else CudaKernels()
+        self.lookahead = lookahead
+        self.timings = {}
+
+    # -- layout ---------------------------------------------------------------------------------
+    def _layout(self, N: int, m: int):
+        tb, g = self.tb, self.g
+        self.N, self.m = N, m
+        self.TC = (N + tb - 1) // tb
+        self.cap = tb - 1
+        self.TE = (m + self.cap - 1) // self.cap
+        self.TR = self.TC + self.TE
+        self.LRt = local_tiles(self.TR, g.P, g.p)
+        self.LCt = local_tiles(self.TC, g.Q, g.q)
+        self.LRmax = local_tiles(self.TR, g.P, 0)
+
+    def local_bytes(self, N: int, m: int) -> int:
+        self._layout(N, m)
+        tb = self.tb
+        return 8 * (self.LRt * tb * self.LCt * tb + 2 * self.g.P * self.LRmax * tb * tb + self.LCt * tb * tb)
+
+    # -- the sweep --------------------------------------------------------------------------------
+    def solve(self, coords: Sequence, z, targets, params, n_procs: int, i_pred: int, metric: int):
+        """coords / z / targets: host arrays replicated on every rank.  Returns (pred, var, info) as numpy
+        arrays / int, identical on every rank; info > 0 = order of the first non-PD leading minor."""
+        K, g, tb = self.k, self.g, self.tb
+        params = np.asarray(params, dtype=np.float64)
+        coords_d = [K.to_device(np.ascontiguousarray(np.asarray(c, dtype=np.float64))) for c in coords[:n_procs]]
+        z_d = K.to_device(np.ascontiguousarray(np.hstack([np.asarray(v, dtype=np.float64) for v in z[:n_procs]])))
+        t_d = K.to_device(np.ascontiguousarray(np.asarray(targets, dtype=np.float64)))
+        N, m = int(z_d.shape[0]), int(t_d.shape[0])
+        self._layout(N, m)
+        P, Q, p, q = g.P, g.Q, g.p, g.q
+        TC, LRt, LCt = self.TC, self.LRt, self.LCt
+        sig = params[i_pred] if n_procs == 2 else params[0]
+        nug = params[8 + i_pred] if n_procs == 2 else params[3]
+        c0 = sig * sig + nug
+
+        local = K.empty(max(LRt * tb, 1), max(LCt * tb, 1))
+        stage = K.empty(2, P, max(self.LRmax, 1), tb, tb)          # double-buffered gathered panel
+        bgather = K.empty(max(LCt, 1), tb, tb)                      # B operand: panel tiles of my tile columns
+        packs = [K.empty(K.pack_size(tb)) for _ in range(2)]
+        info = K.zeros(max(TC, 1), dtype=torch.int32)
+        ev = {"t0": self._mark()}
+        K.assemble(coords_d, t_d, z_d, params, n_procs, i_pred, metric, tb, g, local)
+        ev["t1"] = self._mark()
+
+        main_done = [None, None]  # main_done[b]: last trailing update that read stage[b] has finished
+        panel_ready = self._factor_panel(0, local, stage[0], packs[0], info, None, None) if TC else None
+        for k in range(TC):
+            buf = k % 2
+            nxt = None
+            if self.lookahead and k + 1 < TC:
+                # column k+1 first (its owners), then its panel, all on the panel stream
+                nxt = self._factor_panel(k + 1, local, stage[1 - buf], packs[1 - buf], info,
+                                         (k, stage[buf], panel_ready), main_done[1 - buf])
+            with K.stream("main"):
+                K.wait(panel_ready)
+                skip = (k + 1) if (self.lookahead and k + 1 < TC) else None
+                self._trailing_update(k, local, stage[buf], bgather, skip_col=skip)
+                main_done[buf] = K.event()
+            if not self.lookahead and k + 1 < TC:
+                nxt = self._factor_panel(k + 1, local, stage[1 - buf], packs[1 - buf], info, None, main_done[buf])
+            panel_ready = nxt
+        ev["t2"] = self._mark()
+
+        # -- predictions from the target tiles
+        part = K.zeros(2, max(m, 1))
+        with K.stream("main"):
+            for li in range(LRt):
+                I = li * P + p
+                if I < TC or LCt == 0:
+                    continue
+                t_lo = (I - TC) * self.cap
+                nt = min(self.cap, m - t_lo)
+                rows = local[li * tb: li * tb + nt, : LCt * tb]
+                y = local[li * tb + tb - 1, : LCt * tb]
+                vy, vv = K.row_dots(rows, y)
+                part[0, t_lo: t_lo + nt] = vy
+                part[1, t_lo: t_lo + nt] = vv
+            if g.world > 1:
+                allp = K.empty(g.world, 2, max(m, 1))
+                dist.all_gather_into_tensor(allp, part)
+                dist.all_reduce(info, op=dist.ReduceOp.MAX)
+                total = allp[0].clone()
+                for r in range(1, g.world):  # fixed rank order
+                    total += allp[r]
+            else:
+                total = part
+        ev["t3"] = self._mark()
+        K.sync()
+        pred = total[0, :m].cpu().numpy()
+        var = c0 - total[1, :m].cpu().numpy()
+        inf = info.cpu().numpy()
+        bad = np.nonzero(inf[:TC] > 0)[0]
+        first_bad = int(bad[0] * tb + inf[bad[0]]) if bad.size else 0
+        if first_bad > N:
+            first_bad = 0  # cannot happen: the pad is the identity
+        self.timings = self._elapsed(ev)
+        self._keep = (local, stage)  # factor stays resident (logdet / diagnostics)
+        return pred, var, first_bad
+
+    def logdet(self) -> float:
+        """2 sum log L_kk over the diagonal tiles (after solve()), summed over ranks."""
+        local, _ = self._keep
+        g, tb = self.g, self.tb
+        s = self.k.zeros(1)
+        for k in range(self.TC):
+            if k % g.P == g.p and k % g.Q == g.q:
+                li, lj = k // g.P, k // g.Q
+                d = torch.diagonal(local[li * tb:(li + 1) * tb, lj * tb:(lj + 1) * tb])
+                s += 2.0 * torch.log(d).sum()
+        if g.world > 1:
+            dist.all_reduce(s)
+        return float(s.item())
+
+    # -- pieces -----------------------------------------------------------------------------------
+    def _factor_panel(self, k: int, local, stage_b, pack, info, pending, stage_free):
+        """Panel stream: [apply `pending` = (k-1, its stage, its ready event) to column k on its owners] ->
+        potrf(k,k) -> broadcast -> TRSM of the rows below -> gather the panel on every rank.
+        Returns the event after which stage_b holds panel k everywhere."""
+        K, g, tb = self.k, self.g, self.tb
+        P, Q, p, q = g.P, g.Q, g.p, g.q
+        qk, pk = k % Q, k % P
+        ljk = k // Q
+        with K.stream("panel"):
+            K.wait(stage_free)
+            if pending is not None:
+                kp, stage_prev, ready_prev = pending
+                K.wait(ready_prev)
+                if q == qk:  # bring column k up to date with panel k-1 (rows I >= k)
+                    li0 = first_local_after(k - 1, P, p)
+                    if li0 < self.LRt:
+                        A = stage_prev[p, li0: self.LRt].view(-1, tb)
+                        B = stage_prev[k % P, k // P]
+                        C = local[li0 * tb: self.LRt * tb, ljk * tb:(ljk + 1) * tb]
+                        K.update(A, B, C, tb, li0 * P + p, P, k, Q)
+            if q == qk:
+                if p == pk:
+                    lik = k // P
+                    K.potrf_tile(local[lik * tb:(lik + 1) * tb, ljk * tb:(ljk + 1) * tb], pack, info[k: k + 1])
+                if P > 1:
+                    dist.broadcast(pack, src=g.rank_of(pk, qk), group=g.col_groups[qk])
+                li0 = first_local_after(k, P, p)
+                if li0 < self.LRt:
+                    rows = local[li0 * tb: self.LRt * tb, ljk * tb:(ljk + 1) * tb]
+                    K.trsm(pack, tb, rows)
+                    stage_b[p, li0: self.LRt].view(-1, tb).copy_(rows)
+            if g.world > 1:
+                for pp in range(P):
+                    l0, l1 = first_local_after(k, P, pp), local_tiles(self.TR, P, pp)
+                    if l0 < l1:
+                        dist.broadcast(stage_b[pp, l0:l1], src=g.rank_of(pp, qk))
+            return K.event()
+
+    def _trailing_update(self, k: int, local, stage_b, bgather, skip_col=None) -> None:
+        """A_IJ -= L_Ik L_Jk^T on my tiles with I > k, J > k (J <= I), minus column `skip_col` (done by look-ahead)."""
+        K, g, tb = self.k, self.g, self.tb
+        P, Q, p, q = g.P, g.Q, g.p, g.q
+        li0 = first_local_after(k, P, p)
+        lj0 = first_local_after(k, Q, q)
+        if skip_col is not None and lj0 < self.LCt and lj0 * Q + q == skip_col:
+            lj0 += 1
+        if li0 >= self.LRt or lj0 >= self.LCt:
+            return
+        # my rows can only see columns J <= I_max; extra (target) tiles see all of them
+        A = stage_b[p, li0: self.LRt].view(-1, tb)
+        nb = self.LCt - lj0
+        idx_p = [(lj * Q + q) % P for lj in range(lj0, self.LCt)]
+        idx_t = [(lj * Q + q) // P for lj in range(lj0, self.LCt)]
+        if P == 1 and Q == 1:
+            B = stage_b[0, idx_t[0]: idx_t[0] + nb].view(-1, tb)
+        else:
+            flat = stage_b.view(P * stage_b.shape[1], tb, tb)
+            sel = torch.tensor([a * stage_b.shape[1] + b for a, b in zip(idx_p, idx_t)], dtype=torch.int64,
+                               device=stage_b.device)
+            torch.index_select(flat, 0, sel, out=bgather[:nb])
+            B = bgather[:nb].view(-1, tb)
+        C = local[li0 * tb: self.LRt * tb, lj0 * tb: self.LCt * tb]
+        K.update(A, B, C, tb, li0 * P + p, P, lj0 * Q + q, Q)
+
+    # -- timing -----------------------------------------------------------------------------------
+    def _mark(self):
+        if isinstance(self.k, CudaKernels):
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(self.k.main)
+            return e
+        import time
+        return time.perf_counter()
+
+    def _elapsed(self, ev) -> dict:
+        names = [("assemble", "t0", "t1"), ("factor_solve", "t1", "t2"), ("reduce", "t2", "t3")]
+        out = {}
+        for name, a, b in names:
+            if isinstance(ev[a], float):
+                out[name + "_ms"] = 1e3 * (ev[b] - ev[a])
+            else:
+                out[name + "_ms"] = ev[a].elapsed_time(ev[b])
+        return out

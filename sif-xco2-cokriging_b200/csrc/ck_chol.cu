@@ -50,7 +50,12 @@ struct GemmArgs {
   int mode;        // 0: C = A B^T, 1: C = C - A B^T
   int lower_only;  // 1: C square, triangular grid over the tiles intersecting the lower triangle;
                    // 2: C rectangular (M >= N, diagonal at the top-left), 2-D grid, tiles above the diagonal exit;
-                   // in both cases entries with col > row are not stored
+                   // 3: C is the local part of a 2-D block-cyclic matrix (square tiles of `tb` elements): local
+                   //    tile (li, lj) is global tile (gi0 + li*gis, gj0 + lj*gjs); tiles with J > I exit, tiles
+                   //    with J == I keep the lower triangle of the tile;
+                   // in all cases entries above the (global) diagonal are not stored
+  int tb = 0;
+  long long gi0 = 0, gis = 1, gj0 = 0, gjs = 1;
 };
 
 // CTA tile (32*WM) x (32*WN); each of the 8 warps owns a 32 x 32 sub-tile = 4 x 4 DMMA tiles.
@@ -75,6 +80,18 @@ __global__ void __launch_bounds__(G_THREADS, 2) ck_gemm_nt_kernel(GemmArgs g) {
     if (g.lower_only == 2 && tn * BN > tm * BM + BM - 1) return;  // rectangular C: tile entirely above the diagonal
   }
   const long long m0 = tm * BM, n0 = tn * BN;
+  // store mask: entry (r, c) of C is kept iff !masked or (c - coff) <= (r - roff)
+  bool masked = g.lower_only != 0;
+  long long roff = 0, coff = 0;
+  if (g.lower_only == 3) {
+    const long long li = m0 / g.tb, lj = n0 / g.tb;
+    const long long I = g.gi0 + li * g.gis, J = g.gj0 + lj * g.gjs;
+    if (J > I) return;
+    roff = li * g.tb;
+    coff = lj * g.tb;
+    masked = (J == I);
+    if (masked && (n0 - coff) > (m0 - roff) + BM - 1) return;
+  }
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp / WN, wn = warp % WN;
   const int g4 = lane >> 2, t4 = lane & 3;
@@ -177,8 +194,8 @@ __global__ void __launch_bounds__(G_THREADS, 2) ck_gemm_nt_kernel(GemmArgs g) {
       const long long r = crow0 + mi * 8, c = ccol0 + ni * 8;
       if (r >= g.M) continue;
       double* p = g.C + r * g.ldc + c;
-      const bool ok0 = c < g.N && (!g.lower_only || c <= r);
-      const bool ok1 = c + 1 < g.N && (!g.lower_only || c + 1 <= r);
+      const bool ok0 = c < g.N && (!masked || c - coff <= r - roff);
+      const bool ok1 = c + 1 < g.N && (!masked || c + 1 - coff <= r - roff);
       if (VEC16 && ok0 && ok1) {
         *reinterpret_cast<double2*>(p) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
       } else {
@@ -358,13 +375,16 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
   return r;
 }
 
-// one CTA per target row c:  pred[c] = V_c . y ;  var[c] = c0 - |V_c|^2
+// one CTA per target row c:  pred[c] = V_c . y_c ;  var[c] = c0 + sgn |V_c|^2   (y_c = y + c * ldy; ldy = 0: one shared y)
+// sgn = -1: simple-cokriging variance; c0 = 0, sgn = +1: partial row sums of the block-cyclic solve (ck_row_dots).
 __global__ void __launch_bounds__(256) ck_predict_rows_kernel(const double* __restrict__ V, long long ldv, long long n,
-                                                              const double* __restrict__ y, double c0,
-                                                              double* __restrict__ pred, double* __restrict__ var) {
+                                                              const double* __restrict__ ybase, long long ldy, double c0,
+                                                              double sgn, double* __restrict__ pred,
+                                                              double* __restrict__ var) {
   __shared__ double red[256];
   const long long c = blockIdx.x;
   const double* v = V + c * ldv;
+  const double* y = ybase + c * ldy;
   double s2 = 0.0, sy = 0.0;
   for (long long k = threadIdx.x; k < n; k += 256) {
     const double x = v[k];
@@ -375,7 +395,7 @@ __global__ void __launch_bounds__(256) ck_predict_rows_kernel(const double* __re
   sy = block_sum<256>(sy, red);
   if (threadIdx.x == 0) {
     pred[c] = sy;
-    var[c] = c0 - s2;
+    var[c] = c0 + sgn * s2;
   }
 }
 
@@ -569,7 +589,7 @@ extern "C" int ck_potrs_predict(const double* l, ck_i64 n, ck_i64 ld, const void
   int rc = ck_trsm_lower(l, n, ld, ws, cpd, m + 1, ld_c, stream);
   if (rc) return rc;
   if (m > 0) {
-    ck_predict_rows_kernel<<<(unsigned)m, 256, 0, st>>>(cpd, ld_c, n, cpd + m * ld_c, c0, pred, var);
+    ck_predict_rows_kernel<<<(unsigned)m, 256, 0, st>>>(cpd, ld_c, n, cpd + m * ld_c, 0, c0, -1.0, pred, var);
     CK_LAUNCH_CHECK();
   }
   return CK_OK;
@@ -598,5 +618,48 @@ extern "C" int ck_nll(const double* xy0, ck_i64 n0, const double* xy1, ck_i64 n1
   ck_diag_reduce_kernel<<<1, 1024, 0, st>>>(sigma, ld, n, 0, out + 2);
   ck_nll_combine_kernel<<<1, 1, 0, st>>>(out, n);
   CK_LAUNCH_CHECK_N(3);
+  return CK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// building blocks of the multi-GPU (2-D block-cyclic) factorisation -- orchestrated per rank by
+// cokrig_b200/parallel.py over torch.distributed / NCCL
+// ------------------------------------------------------------------------------------------------
+extern "C" int ck_gemm_nt(const double* a, ck_i64 lda, const double* b, ck_i64 ldb, double* c, ck_i64 ldc, ck_i64 m, ck_i64 n,
+                          ck_i64 k, int subtract, void* stream) {
+  CK_REQUIRE(m >= 0 && n >= 0 && k >= 0, "negative size");
+  if (m == 0 || n == 0) return CK_OK;
+  CK_REQUIRE(a && b && c, "null pointer");
+  CK_REQUIRE(lda >= k && ldb >= k && ldc >= n, "leading dimension too small");
+  GemmArgs g;
+  g.A = a; g.lda = lda; g.B = b; g.ldb = ldb; g.C = c; g.ldc = ldc;
+  g.M = m; g.N = n; g.K = k; g.mode = subtract ? 1 : 0; g.lower_only = 0;
+  return gemm_launch<4, 2>(g, ck_stream(stream));
+}
+
+extern "C" int ck_mg_update(const double* a, ck_i64 lda, const double* b, ck_i64 ldb, double* c, ck_i64 ldc, ck_i64 m,
+                            ck_i64 n, ck_i64 k, ck_i64 tb, ck_i64 row_tile0, ck_i64 row_tile_step, ck_i64 col_tile0,
+                            ck_i64 col_tile_step, void* stream) {
+  CK_REQUIRE(m >= 0 && n >= 0 && k >= 0, "negative size");
+  if (m == 0 || n == 0) return CK_OK;
+  CK_REQUIRE(a && b && c, "null pointer");
+  CK_REQUIRE(lda >= k && ldb >= k && ldc >= n, "leading dimension too small");
+  CK_REQUIRE(tb > 0 && tb % 128 == 0, "tile size must be a multiple of 128 (got %lld)", (long long)tb);
+  CK_REQUIRE(m % tb == 0 && n % tb == 0, "m and n must be whole tiles");
+  CK_REQUIRE(row_tile_step >= 1 && col_tile_step >= 1 && row_tile0 >= 0 && col_tile0 >= 0, "bad tile map");
+  GemmArgs g;
+  g.A = a; g.lda = lda; g.B = b; g.ldb = ldb; g.C = c; g.ldc = ldc;
+  g.M = m; g.N = n; g.K = k; g.mode = 1; g.lower_only = 3;
+  g.tb = (int)tb; g.gi0 = row_tile0; g.gis = row_tile_step; g.gj0 = col_tile0; g.gjs = col_tile_step;
+  return gemm_launch<4, 2>(g, ck_stream(stream));
+}
+
+extern "C" int ck_row_dots(const double* v, ck_i64 ldv, ck_i64 nrows, ck_i64 ncols, const double* y, ck_i64 ldy,
+                           double* out_vy, double* out_vv, void* stream) {
+  CK_REQUIRE(nrows >= 0 && ncols >= 0, "negative size");
+  if (nrows == 0) return CK_OK;
+  CK_REQUIRE(v && y && out_vy && out_vv, "null pointer");
+  ck_predict_rows_kernel<<<(unsigned)nrows, 256, 0, ck_stream(stream)>>>(v, ldv, ncols, y, ldy, 0.0, 1.0, out_vy, out_vv);
+  CK_LAUNCH_CHECK();
   return CK_OK;
 }

@@ -50,4 +50,8 @@ int ck_unpack_params(const double* params, int n_procs, CkParams* out);
 // Block (i, j) of the joint model: i == j -> covariance(i, ., use_nugget), else cross_covariance(i, j, .)
 int ck_block_matern(const CkParams& p, int i, int j, int use_nugget, CkMatern* out);
 
+// One block of distances (value = 0) or covariances (value = 1) from coordinates (ck_matern.cu).
+int ck_block_launch(const double* xy1, ck_i64 n1, const double* xy2, ck_i64 n2, int metric, const CkMatern& P, int value,
+                    double* out, ck_i64 ld, double* out_t, ck_i64 ld_t, int symmetric, cudaStream_t st);
+
 static inline cudaStream_t ck_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }

@@ -136,7 +136,7 @@ static void launch_mode(const CkMatern& P, dim3 grid, cudaStream_t st, const dou
 #undef CK_K1
 }
 
-static int block_launch(const double* xy1, ck_i64 n1, const double* xy2, ck_i64 n2, int metric, const CkMatern& P, int value,
+int ck_block_launch(const double* xy1, ck_i64 n1, const double* xy2, ck_i64 n2, int metric, const CkMatern& P, int value,
                         double* out, ck_i64 ld, double* out_t, ck_i64 ld_t, int symmetric, cudaStream_t st) {
   CK_REQUIRE(n1 >= 0 && n2 >= 0, "negative size");
   if (n1 == 0 || n2 == 0) return CK_OK;
@@ -198,7 +198,7 @@ extern "C" int ck_distance_block(const double* xy1, ck_i64 n1, const double* xy2
                                  ck_i64 ld, void* stream) {
   CkMatern P;
   ck_matern_setup(&P, 1.0, 0.5, 1.0, 0.0);
-  return block_launch(xy1, n1, xy2, n2, metric, P, 0, out, ld, nullptr, 0, 0, ck_stream(stream));
+  return ck_block_launch(xy1, n1, xy2, n2, metric, P, 0, out, ld, nullptr, 0, 0, ck_stream(stream));
 }
 
 extern "C" int ck_matern_block(const double* xy1, ck_i64 n1, const double* xy2, ck_i64 n2, int metric, double scale,
@@ -206,7 +206,7 @@ extern "C" int ck_matern_block(const double* xy1, ck_i64 n1, const double* xy2, 
                                ck_i64 ld_t, int symmetric, void* stream) {
   CkMatern P;
   CK_REQUIRE(ck_matern_setup(&P, scale, nu, len_scale, nugget) == 0, "invalid Matern parameters nu=%g len_scale=%g", nu, len_scale);
-  return block_launch(xy1, n1, xy2, n2, metric, P, 1, out, ld, out_t, ld_t, symmetric, ck_stream(stream));
+  return ck_block_launch(xy1, n1, xy2, n2, metric, P, 1, out, ld, out_t, ld_t, symmetric, ck_stream(stream));
 }
 
 extern "C" int ck_joint_cov(const double* xy0, ck_i64 n0, const double* xy1, ck_i64 n1, const double* params, int n_procs,
@@ -220,12 +220,12 @@ extern "C" int ck_joint_cov(const double* xy0, ck_i64 n0, const double* xy1, ck_
   cudaStream_t st = ck_stream(stream);
   CkMatern P;
   if ((rc = ck_block_matern(p, 0, 0, 1, &P))) return rc;
-  if ((rc = block_launch(xy0, n0, xy0, n0, metric, P, 1, sigma, ld, nullptr, 0, 1, st))) return rc;
+  if ((rc = ck_block_launch(xy0, n0, xy0, n0, metric, P, 1, sigma, ld, nullptr, 0, 1, st))) return rc;
   if (n_procs == 2) {
     if ((rc = ck_block_matern(p, 1, 1, 1, &P))) return rc;
-    if ((rc = block_launch(xy1, n1, xy1, n1, metric, P, 1, sigma + n0 * ld + n0, ld, nullptr, 0, 1, st))) return rc;
+    if ((rc = ck_block_launch(xy1, n1, xy1, n1, metric, P, 1, sigma + n0 * ld + n0, ld, nullptr, 0, 1, st))) return rc;
     if ((rc = ck_block_matern(p, 0, 1, 0, &P))) return rc;
-    if ((rc = block_launch(xy0, n0, xy1, n1, metric, P, 1, sigma + n0, ld, sigma + n0 * ld, ld, 0, st))) return rc;
+    if ((rc = ck_block_launch(xy0, n0, xy1, n1, metric, P, 1, sigma + n0, ld, sigma + n0 * ld, ld, 0, st))) return rc;
   }
   return CK_OK;
 }
@@ -246,7 +246,7 @@ extern "C" int ck_cross_cov(const double* xy0, ck_i64 n0, const double* xy1, ck_
   for (int j = 0; j < n_procs; ++j) {
     CkMatern P;
     if ((rc = ck_block_matern(p, i_pred, j, 1, &P))) return rc;
-    if ((rc = block_launch(xyp, m, xy[j], nn[j], metric, P, 1, cpd + off, ld, nullptr, 0, 0, st))) return rc;
+    if ((rc = ck_block_launch(xyp, m, xy[j], nn[j], metric, P, 1, cpd + off, ld, nullptr, 0, 0, st))) return rc;
     off += nn[j];
   }
   return CK_OK;

@@ -24,6 +24,11 @@ static inline VarioGeom vario_geom(long long na, long long nb) {
   g.tb = (nb + VB - 1) / VB;
   return g;
 }
+// tile-row range [t0, t1) of one call: (0, <0) = all rows of A (single-GPU); multi-GPU ranks pass their share
+static inline bool vario_range(const VarioGeom& g, long long* t0, long long* t1) {
+  if (*t1 < 0) { *t0 = 0; *t1 = g.ta; }
+  return *t0 >= 0 && *t0 <= *t1 && *t1 <= g.ta;
+}
 static inline int vario_warps(int n_bins) {
   int w = V_SMEM_BUDGET / (n_bins * 32 * 12);
   if (w > V_MAX_WARPS) w = V_MAX_WARPS;
@@ -43,9 +48,9 @@ __global__ void __launch_bounds__(256) ck_vario_minmax_kernel(const double* __re
                                                               const double* __restrict__ xyb, long long nb,
                                                               int same_field, double max_dist,
                                                               unsigned long long* __restrict__ out,
-                                                              unsigned long long* __restrict__ tile_mm) {
-  const long long a0 = (long long)blockIdx.y * VA, b0 = (long long)blockIdx.x * VB;
-  const long long tile = (long long)blockIdx.y * gridDim.x + blockIdx.x;
+                                                              unsigned long long* __restrict__ tile_mm, long long ty0) {
+  const long long a0 = (ty0 + blockIdx.y) * VA, b0 = (long long)blockIdx.x * VB;
+  const long long tile = (ty0 + blockIdx.y) * gridDim.x + blockIdx.x;
   if (same_field && b0 + VB - 1 <= a0) {  // tile entirely on/below the diagonal
     if (threadIdx.x == 0) { tile_mm[2 * tile] = 0x7FF0000000000000ULL; tile_mm[2 * tile + 1] = 0ULL; }
     return;
@@ -114,9 +119,9 @@ __global__ void __launch_bounds__(256) ck_vario_candidates_kernel(const double* 
                                                                   int same_field, double dlim, double lo, double hi,
                                                                   const unsigned long long* __restrict__ tile_mm,
                                                                   ck_i64* __restrict__ pairs, long long capacity,
-                                                                  unsigned long long* __restrict__ count) {
-  const long long a0 = (long long)blockIdx.y * VA, b0 = (long long)blockIdx.x * VB;
-  const long long tile = (long long)blockIdx.y * gridDim.x + blockIdx.x;
+                                                                  unsigned long long* __restrict__ count, long long ty0) {
+  const long long a0 = (ty0 + blockIdx.y) * VA, b0 = (long long)blockIdx.x * VB;
+  const long long tile = (ty0 + blockIdx.y) * gridDim.x + blockIdx.x;
   const double tmn = __longlong_as_double((long long)tile_mm[2 * tile]);
   const double tmx = __longlong_as_double((long long)tile_mm[2 * tile + 1]);
   if (!(tmn <= lo) && !(tmx >= hi)) return;
@@ -168,8 +173,13 @@ extern "C" size_t ck_vario_minmax_workspace_bytes(ck_i64 na, ck_i64 nb) {
   return (size_t)g.ta * g.tb * 16 + 256;
 }
 
+extern "C" ck_i64 ck_vario_tile_rows(ck_i64 na) { return na > 0 ? (na + VA - 1) / VA : 0; }
+extern "C" ck_i64 ck_vario_tile_cols(ck_i64 nb) { return nb > 0 ? (nb + VB - 1) / VB : 0; }
+extern "C" int ck_vario_tile_shape(int* va, int* vb) { if (va) *va = VA; if (vb) *vb = VB; return CK_OK; }
+
 extern "C" int ck_vario_minmax(const double* xya, ck_i64 na, const double* xyb, ck_i64 nb, int metric, int same_field,
-                               double max_dist, double* out, void* ws, void* stream) {
+                               double max_dist, ck_i64 tile_row_begin, ck_i64 tile_row_end, double* out, void* ws,
+                               void* stream) {
   CK_REQUIRE(na >= 0 && nb >= 0 && out, "bad argument");
   CK_REQUIRE(metric == CK_METRIC_EUCLID || metric == CK_METRIC_HAVERSINE, "bad metric %d", metric);
   CK_REQUIRE(!same_field || na == nb, "same_field needs na == nb");
@@ -179,21 +189,27 @@ extern "C" int ck_vario_minmax(const double* xya, ck_i64 na, const double* xyb, 
   if (na > 0 && nb > 0) {
     CK_REQUIRE(xya && xyb && ws, "null pointer");
     const VarioGeom g = vario_geom(na, nb);
-    CK_REQUIRE(g.ta <= 65535, "na too large");
-    dim3 grid((unsigned)g.tb, (unsigned)g.ta);
-    unsigned long long* mm = static_cast<unsigned long long*>(ws);
-    const double dlim = vario_dlim(metric, max_dist);
-    if (metric == CK_METRIC_HAVERSINE) ck_vario_minmax_kernel<CK_METRIC_HAVERSINE><<<grid, 256, 0, st>>>(xya, na, xyb, nb, same_field, dlim, o, mm);
-    else ck_vario_minmax_kernel<CK_METRIC_EUCLID><<<grid, 256, 0, st>>>(xya, na, xyb, nb, same_field, dlim, o, mm);
+    long long t0 = tile_row_begin, t1 = tile_row_end;
+    CK_REQUIRE(vario_range(g, &t0, &t1), "bad tile-row range [%lld, %lld) of %lld", (long long)tile_row_begin, (long long)tile_row_end, g.ta);
+    CK_REQUIRE(t1 - t0 <= 65535, "na too large");
+    if (t1 > t0) {
+      dim3 grid((unsigned)g.tb, (unsigned)(t1 - t0));
+      unsigned long long* mm = static_cast<unsigned long long*>(ws);
+      const double dlim = vario_dlim(metric, max_dist);
+      if (metric == CK_METRIC_HAVERSINE) ck_vario_minmax_kernel<CK_METRIC_HAVERSINE><<<grid, 256, 0, st>>>(xya, na, xyb, nb, same_field, dlim, o, mm, t0);
+      else ck_vario_minmax_kernel<CK_METRIC_EUCLID><<<grid, 256, 0, st>>>(xya, na, xyb, nb, same_field, dlim, o, mm, t0);
+      CK_LAUNCH_CHECK();
+    }
   }
   ck_vario_minmax_final_kernel<<<1, 1, 0, st>>>(o);
-  CK_LAUNCH_CHECK_N((na > 0 && nb > 0) ? 3 : 2);
+  CK_LAUNCH_CHECK_N(2);
   return CK_OK;
 }
 
 extern "C" int ck_vario_candidates(const double* xya, ck_i64 na, const double* xyb, ck_i64 nb, int metric, int same_field,
-                                   double max_dist, double lo, double hi, const void* ws, ck_i64* pairs, ck_i64 capacity,
-                                   unsigned long long* count, void* stream) {
+                                   double max_dist, double lo, double hi, ck_i64 tile_row_begin, ck_i64 tile_row_end,
+                                   const void* ws, ck_i64* pairs, ck_i64 capacity, unsigned long long* count,
+                                   void* stream) {
   CK_REQUIRE(na >= 0 && nb >= 0 && pairs && count && capacity >= 0, "bad argument");
   CK_REQUIRE(metric == CK_METRIC_EUCLID || metric == CK_METRIC_HAVERSINE, "bad metric %d", metric);
   cudaStream_t st = ck_stream(stream);
@@ -201,11 +217,14 @@ extern "C" int ck_vario_candidates(const double* xya, ck_i64 na, const double* x
   if (na == 0 || nb == 0) return CK_OK;
   CK_REQUIRE(xya && xyb && ws, "null pointer");
   const VarioGeom g = vario_geom(na, nb);
-  dim3 grid((unsigned)g.tb, (unsigned)g.ta);
+  long long t0 = tile_row_begin, t1 = tile_row_end;
+  CK_REQUIRE(vario_range(g, &t0, &t1), "bad tile-row range [%lld, %lld) of %lld", (long long)tile_row_begin, (long long)tile_row_end, g.ta);
+  if (t1 == t0) return CK_OK;
+  dim3 grid((unsigned)g.tb, (unsigned)(t1 - t0));
   const unsigned long long* mm = static_cast<const unsigned long long*>(ws);
   const double dlim = vario_dlim(metric, max_dist);
-  if (metric == CK_METRIC_HAVERSINE) ck_vario_candidates_kernel<CK_METRIC_HAVERSINE><<<grid, 256, 0, st>>>(xya, na, xyb, nb, same_field, dlim, lo, hi, mm, pairs, capacity, count);
-  else ck_vario_candidates_kernel<CK_METRIC_EUCLID><<<grid, 256, 0, st>>>(xya, na, xyb, nb, same_field, dlim, lo, hi, mm, pairs, capacity, count);
+  if (metric == CK_METRIC_HAVERSINE) ck_vario_candidates_kernel<CK_METRIC_HAVERSINE><<<grid, 256, 0, st>>>(xya, na, xyb, nb, same_field, dlim, lo, hi, mm, pairs, capacity, count, t0);
+  else ck_vario_candidates_kernel<CK_METRIC_EUCLID><<<grid, 256, 0, st>>>(xya, na, xyb, nb, same_field, dlim, lo, hi, mm, pairs, capacity, count, t0);
   CK_LAUNCH_CHECK();
   return CK_OK;
 }
@@ -228,7 +247,7 @@ struct VarioBinArgs {
 };
 
 template <int METRIC>
-__global__ void __launch_bounds__(256) ck_vario_bin_kernel(VarioBinArgs g, int nwarps) {
+__global__ void __launch_bounds__(256) ck_vario_bin_kernel(VarioBinArgs g, int nwarps, long long ty0) {
   extern __shared__ __align__(16) unsigned char vsm[];
   const int nb_ = g.n_bins;
   double* hsum = reinterpret_cast<double*>(vsm);                                  // [warp][bin][lane]
@@ -236,8 +255,8 @@ __global__ void __launch_bounds__(256) ck_vario_bin_kernel(VarioBinArgs g, int n
   double* edges = reinterpret_cast<double*>(hcnt + (size_t)nwarps * nb_ * 32);   // n_bins + 1
   __shared__ CkPoint pa[VA], pb[VB];
   __shared__ double ra[VA], rb[VB];
-  const long long a0 = (long long)blockIdx.y * VA, b0 = (long long)blockIdx.x * VB;
-  const long long tile = (long long)blockIdx.y * gridDim.x + blockIdx.x;
+  const long long a0 = (ty0 + blockIdx.y) * VA, b0 = (long long)blockIdx.x * VB;
+  const long long tile = (ty0 + blockIdx.y) * gridDim.x + blockIdx.x;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int nthreads = nwarps * 32;
   const bool skip = g.same_field && (b0 + VB - 1 <= a0);
@@ -371,13 +390,30 @@ extern "C" size_t ck_vario_bin_workspace_bytes(ck_i64 na, ck_i64 nb, int n_bins)
   return align256((size_t)(n_bins + 1) * 8) + align256(tiles * n_bins * 8) + align256(tiles * n_bins * 4);
 }
 
-extern "C" int ck_vario_bin(const double* xya, const double* va, ck_i64 na, double mean_a, const double* xyb,
-                            const double* vb, ck_i64 nb, double mean_b, int metric, int same_field, int covariogram,
-                            double max_dist, const double* edges, int n_bins, unsigned long long* counts, double* sums,
-                            ck_i64* flagged, ck_i64 flag_capacity, unsigned long long* flag_count, void* ws,
-                            void* stream) {
-  CK_REQUIRE(na >= 0 && nb >= 0, "negative size");
-  CK_REQUIRE(n_bins >= 1 && edges && counts && sums && ws, "bad argument");
+// workspace layout: [edges (n_bins+1 doubles)] [tile_sums: tiles x n_bins doubles] [tile_counts: tiles x n_bins u32]
+struct VarioWs {
+  double* edges; double* tile_sums; unsigned int* tile_counts; size_t tiles;
+};
+static inline VarioWs vario_ws(void* ws, ck_i64 na, ck_i64 nb, int n_bins) {
+  const VarioGeom geo = vario_geom(na, nb);
+  VarioWs w;
+  w.tiles = (size_t)geo.ta * geo.tb;
+  unsigned char* b = static_cast<unsigned char*>(ws);
+  w.edges = reinterpret_cast<double*>(b);
+  w.tile_sums = reinterpret_cast<double*>(b + align256((size_t)(n_bins + 1) * 8));
+  w.tile_counts = reinterpret_cast<unsigned int*>(b + align256((size_t)(n_bins + 1) * 8) + align256(w.tiles * n_bins * 8));
+  return w;
+}
+
+extern "C" size_t ck_vario_bin_partials_offset(int n_bins) { return align256((size_t)(n_bins + 1) * 8); }
+
+extern "C" int ck_vario_bin_tiles(const double* xya, const double* va, ck_i64 na, double mean_a, const double* xyb,
+                                  const double* vb, ck_i64 nb, double mean_b, int metric, int same_field, int covariogram,
+                                  double max_dist, const double* edges, int n_bins, ck_i64 tile_row_begin,
+                                  ck_i64 tile_row_end, ck_i64* flagged, ck_i64 flag_capacity,
+                                  unsigned long long* flag_count, void* ws, void* stream) {
+  CK_REQUIRE(na > 0 && nb > 0, "empty point set");
+  CK_REQUIRE(n_bins >= 1 && edges && ws, "bad argument");
   CK_REQUIRE(metric == CK_METRIC_EUCLID || metric == CK_METRIC_HAVERSINE, "bad metric %d", metric);
   CK_REQUIRE(!same_field || na == nb, "same_field needs na == nb");
   for (int k = 0; k < n_bins; ++k) CK_REQUIRE(edges[k] < edges[k + 1], "edges must be strictly ascending");
@@ -386,43 +422,69 @@ extern "C" int ck_vario_bin(const double* xya, const double* va, ck_i64 na, doub
   cudaStream_t st = ck_stream(stream);
   CK_REQUIRE(!flagged || (flag_count && flag_capacity >= 0), "flag_count is NULL");
   if (flag_count) CK_CUDA(cudaMemsetAsync(flag_count, 0, sizeof(unsigned long long), st));
-  if (na == 0 || nb == 0) {
-    CK_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * n_bins, st));
-    CK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * n_bins, st));
-    return CK_OK;
-  }
   CK_REQUIRE(xya && va && xyb && vb, "null pointer");
   const VarioGeom geo = vario_geom(na, nb);
-  CK_REQUIRE(geo.ta <= 65535, "na too large");
-  const size_t tiles = (size_t)geo.ta * geo.tb;
-  unsigned char* w = static_cast<unsigned char*>(ws);
-  double* edges_dev = reinterpret_cast<double*>(w);
-  double* tile_sums = reinterpret_cast<double*>(w + align256((size_t)(n_bins + 1) * 8));
-  unsigned int* tile_counts = reinterpret_cast<unsigned int*>(w + align256((size_t)(n_bins + 1) * 8) + align256(tiles * n_bins * 8));
-  CK_CUDA(cudaMemcpyAsync(edges_dev, edges, sizeof(double) * (n_bins + 1), cudaMemcpyHostToDevice, st));
+  long long t0 = tile_row_begin, t1 = tile_row_end;
+  CK_REQUIRE(vario_range(geo, &t0, &t1), "bad tile-row range [%lld, %lld) of %lld", (long long)tile_row_begin, (long long)tile_row_end, geo.ta);
+  CK_REQUIRE(t1 - t0 <= 65535, "na too large");
+  const VarioWs w = vario_ws(ws, na, nb, n_bins);
+  // partials of tile rows outside [t0, t1) are ZERO: other ranks own them and the cross-rank combine is a
+  // sum in which every partial has exactly one non-zero contributor (exact, order-free)
+  CK_CUDA(cudaMemsetAsync(w.tile_sums, 0, w.tiles * n_bins * sizeof(double), st));
+  CK_CUDA(cudaMemsetAsync(w.tile_counts, 0, w.tiles * n_bins * sizeof(unsigned int), st));
+  CK_CUDA(cudaMemcpyAsync(w.edges, edges, sizeof(double) * (n_bins + 1), cudaMemcpyHostToDevice, st));
+  if (t1 == t0) return CK_OK;
   VarioBinArgs g;
   g.xya = xya; g.va = va; g.na = na; g.mean_a = mean_a;
   g.xyb = xyb; g.vb = vb; g.nb = nb; g.mean_b = mean_b;
   g.same_field = same_field; g.covariogram = covariogram; g.max_dist = max_dist;
-  g.edges = edges_dev; g.n_bins = n_bins;
+  g.edges = w.edges; g.n_bins = n_bins;
   g.e1 = n_bins >= 2 ? edges[1] : edges[0];
   const double wdt = n_bins >= 2 ? (edges[n_bins] - edges[1]) / (double)(n_bins - 1) : 0.0;
   g.inv_w = wdt > 0.0 ? 1.0 / wdt : 0.0;
-  g.tile_sums = tile_sums; g.tile_counts = tile_counts;
+  g.tile_sums = w.tile_sums; g.tile_counts = w.tile_counts;
   const bool guard = flagged && metric == CK_METRIC_HAVERSINE;  // Euclidean distances are exact: no guard
   g.flagged = guard ? flagged : nullptr; g.flag_capacity = flag_capacity; g.flag_count = flag_count;
   g.guard = CK_VARIO_GUARD; g.dlim = guard ? vario_dlim(metric, max_dist) : max_dist;
   const size_t smem = (size_t)nwarps * n_bins * 32 * 12 + (size_t)(n_bins + 1) * 8 + 16;
-  dim3 grid((unsigned)geo.tb, (unsigned)geo.ta);
+  dim3 grid((unsigned)geo.tb, (unsigned)(t1 - t0));
   if (metric == CK_METRIC_HAVERSINE) {
     CK_CUDA(cudaFuncSetAttribute(ck_vario_bin_kernel<CK_METRIC_HAVERSINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ck_vario_bin_kernel<CK_METRIC_HAVERSINE><<<grid, nwarps * 32, smem, st>>>(g, nwarps);
+    ck_vario_bin_kernel<CK_METRIC_HAVERSINE><<<grid, nwarps * 32, smem, st>>>(g, nwarps, t0);
   } else {
     CK_CUDA(cudaFuncSetAttribute(ck_vario_bin_kernel<CK_METRIC_EUCLID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ck_vario_bin_kernel<CK_METRIC_EUCLID><<<grid, nwarps * 32, smem, st>>>(g, nwarps);
+    ck_vario_bin_kernel<CK_METRIC_EUCLID><<<grid, nwarps * 32, smem, st>>>(g, nwarps, t0);
   }
   CK_LAUNCH_CHECK();
-  ck_vario_tile_reduce_kernel<<<n_bins, 256, 0, st>>>(tile_sums, tile_counts, (long long)tiles, n_bins, counts, sums);
+  return CK_OK;
+}
+
+extern "C" int ck_vario_bin_reduce(ck_i64 na, ck_i64 nb, int n_bins, const void* ws, unsigned long long* counts,
+                                   double* sums, void* stream) {
+  CK_REQUIRE(na > 0 && nb > 0 && n_bins >= 1 && ws && counts && sums, "bad argument");
+  const VarioWs w = vario_ws(const_cast<void*>(ws), na, nb, n_bins);
+  ck_vario_tile_reduce_kernel<<<n_bins, 256, 0, ck_stream(stream)>>>(w.tile_sums, w.tile_counts, (long long)w.tiles, n_bins,
+                                                                    counts, sums);
   CK_LAUNCH_CHECK();
   return CK_OK;
+}
+
+extern "C" int ck_vario_bin(const double* xya, const double* va, ck_i64 na, double mean_a, const double* xyb,
+                            const double* vb, ck_i64 nb, double mean_b, int metric, int same_field, int covariogram,
+                            double max_dist, const double* edges, int n_bins, unsigned long long* counts, double* sums,
+                            ck_i64* flagged, ck_i64 flag_capacity, unsigned long long* flag_count, void* ws,
+                            void* stream) {
+  CK_REQUIRE(na >= 0 && nb >= 0, "negative size");
+  CK_REQUIRE(n_bins >= 1 && edges && counts && sums && ws, "bad argument");
+  if (na == 0 || nb == 0) {
+    cudaStream_t st = ck_stream(stream);
+    if (flag_count) CK_CUDA(cudaMemsetAsync(flag_count, 0, sizeof(unsigned long long), st));
+    CK_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * n_bins, st));
+    CK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * n_bins, st));
+    return CK_OK;
+  }
+  int rc = ck_vario_bin_tiles(xya, va, na, mean_a, xyb, vb, nb, mean_b, metric, same_field, covariogram, max_dist, edges,
+                              n_bins, 0, -1, flagged, flag_capacity, flag_count, ws, stream);
+  if (rc) return rc;
+  return ck_vario_bin_reduce(na, nb, n_bins, ws, counts, sums, stream);
 }
