@@ -340,7 +340,7 @@ class BlockCyclicCokriging:
                 part[1, t_lo: t_lo + nt] = vv
             if g.world > 1:
                 allp = K.empty(g.world, 2, max(m, 1))
-                dist.all_gather_into_tensor(allp, part)
+                dist.all_gather_into_tensor(allp.view(-1), part.view(-1))
                 dist.all_reduce(info, op=dist.ReduceOp.MAX)
                 total = allp[0].clone()
                 for r in range(1, g.world):  # fixed rank order
