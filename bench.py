@@ -226,6 +226,13 @@ def run_gpu(args, n_per_var: int, m: int) -> None:
             phase_ms[name] += e[k].elapsed_time(e[k + 1]) / args.steps
     clocks = sampler.stop() if sampler else None
     pred_dev = pred.clone()
+    if args.profile:
+        if rank == 0:
+            print(f"profile run: {launches} launches in {args.steps} step(s), {elapsed_ms / args.steps:.1f} ms/step (not a bench value)",
+                  file=sys.stderr)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ---- end to end through the drop-in API with host buffers
     mf = fields.MultiField.from_arrays(coords, z, type="real")
@@ -315,8 +322,11 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=3000, help="points per variable of the CPU sample")
     ap.add_argument("--cpu-m", type=int, default=1000)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--profile", action="store_true",
+                    help="profiling run under ncu (prints no bench line): 1 warm-up step, no e2e / cpu legs")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "b200":
+        args.warmup = 1 if args.profile else max(args.warmup, 3)
     if args.impl == "reference":
         run_reference(args, 2 * args.n, args.m)
     else:

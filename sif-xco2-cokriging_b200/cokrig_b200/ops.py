@@ -233,6 +233,13 @@ VARIO_GUARD = 1.8e-15  # must match CK_VARIO_GUARD (csrc/ck_vario.cu)
 VARIO_LIST_CAPACITY = 1 << 16
 
 
+def vario_tiling(na: int, nb: int):
+    """(tile rows, tile columns, points per tile row, points per tile column) of the K2 pair tiling."""
+    va, vb = ctypes.c_int(0), ctypes.c_int(0)
+    check(lib.ck_vario_tile_shape(ctypes.byref(va), ctypes.byref(vb)), "ck_vario_tile_shape")
+    return int(lib.ck_vario_tile_rows(na)), int(lib.ck_vario_tile_cols(nb)), va.value, vb.value
+
+
 def _read_pairs(pairs: torch.Tensor, count: torch.Tensor, what: str):
     n = int(count.item())
     if n > pairs.shape[0]:

@@ -157,6 +157,13 @@ class MultiField:
         self.n_data = self._count_data()
         return self
 
+    def distribute(self, shard) -> "MultiField":
+        """Multi-GPU (not in the reference): partition the variogram pair tiles of this object over the
+        ranks of `shard` (cokrig_b200.parallel.VarioShard).  Every rank must then call get_variogram /
+        empirical_variograms collectively; all ranks obtain the same bits as a single-GPU run."""
+        self._shard = shard
+        return self
+
     def _apply_timedelta(self, timedelta: int) -> str:
         """Timestamp with the month offset applied, as a string."""
         from datetime import datetime
@@ -192,7 +199,7 @@ class MultiField:
         metric = ops.metric_id(config.dist_units, config.fast_dist)
         centers, edges, counts, sums = _device_variogram(
             self.fields[i].coords, self.fields[i].values, self.fields[j].coords, self.fields[j].values,
-            i == j, metric, config.covariogram, config.max_dist, config.n_bins)
+            i == j, metric, config.covariogram, config.max_dist, config.n_bins, shard=getattr(self, "_shard", None))
         with np.errstate(invalid="ignore", divide="ignore"):
             means = np.where(counts > 0, sums / np.maximum(counts, 1), np.nan)
         df = pd.DataFrame({"bin_center": centers, "bin_mean": means, "bin_count": counts.astype(np.int64)})
@@ -235,13 +242,20 @@ def _bins_from_extrema(min_dist: float, max_dist: float, n_bins: int):
     return centers, edges
 
 
-def _device_variogram(coords_a, values_a, coords_b, values_b, same_field, metric, covariogram, max_dist, n_bins):
+def _device_variogram(coords_a, values_a, coords_b, values_b, same_field, metric, covariogram, max_dist, n_bins,
+                      shard=None):
     va = np.ascontiguousarray(np.asarray(values_a, dtype=float))
     vb = np.ascontiguousarray(np.asarray(values_b, dtype=float))
     ca = np.ascontiguousarray(np.asarray(coords_a, dtype=float))
     cb = np.ascontiguousarray(np.asarray(coords_b, dtype=float))
     Xa, Xb = ops.coords_to_device(ca), ops.coords_to_device(cb)
-    res = ops.vario_extrema(Xa, Xb, metric, same_field, max_dist)
+    part = {}
+    if shard is not None and shard.world > 1:  # row-block partition of the pair tiles
+        part = {"tile_rows": shard.tile_rows(*ops.vario_tiling(len(ca), len(cb)), same_field)}
+    res = ops.vario_extrema(Xa, Xb, metric, same_field, max_dist,
+                            combine=(lambda *t: shard.combine_extrema(*t, device=Xa.device)) if part else None, **part)
+    if part:
+        res["candidates"] = shard.gather_pairs(res["candidates"])
     mn, mx = res["min"], res["max"]
     # re-decide the extrema with libm on the candidate pairs (bit-identical to the reference's values)
     if metric == ops.METRIC_HAVERSINE and res["candidates"] is not None:
@@ -255,7 +269,10 @@ def _device_variogram(coords_a, values_a, coords_b, values_b, same_field, metric
         raise ValueError("no pair of points with a positive distance within max_dist")
     centers, edges = _bins_from_extrema(mn, mx, n_bins)
     counts, sums, flagged = ops.vario_bin(Xa, ops.to_device(va), va.mean(), Xb, ops.to_device(vb), vb.mean(), metric,
-                                          same_field, covariogram, max_dist, edges)
+                                          same_field, covariogram, max_dist, edges,
+                                          combine=shard.combine_partials if part else None, **part)
+    if part:
+        flagged = shard.gather_pairs(flagged)
     if flagged is not None and len(flagged):
         ra, rb = va - va.mean(), vb - vb.mean()
         for a, b in flagged:  # pairs within a few ulp of an edge / max_dist: decide like the reference

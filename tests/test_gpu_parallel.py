@@ -1,0 +1,79 @@
+"""GPU tests of the multi-GPU building blocks (cokrig_b200.parallel with the CUDA kernel set):
+on ONE device the block-cyclic sweep degenerates to a 1 x 1 grid and still runs every mg kernel
+(ck_mg_assemble, ck_mg_update, ck_row_dots, tile potrf / trsm); with >= 2 devices the same checks plus
+the sharded variogram run under torchrun (tools/mg_check.py)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import cokrig_oracle as orc
+from conftest import ROOT, relerr
+
+pytestmark = pytest.mark.gpu
+
+HALF = [1.0, 0.8, 1.5, 1.5, 1.5, 0.3, 0.3, 0.3, 0.02, 0.02, -0.2]
+GENERIC_KM = [1.0, 0.8, 0.75, 1.0, 1.25, 500.0, 500.0, 500.0, 0.02, 0.02, -0.2]
+
+
+def _inputs(metric, n0, n1, m, seed):
+    rng = np.random.default_rng(seed)
+    if metric == 1:
+        coords = [np.c_[rng.uniform(25, 50, n), rng.uniform(-120, -70, n)] for n in (n0, n1)]
+        targets = np.c_[rng.uniform(25, 50, m), rng.uniform(-120, -70, m)]
+    else:
+        coords = [rng.uniform(0, 1, (n, 2)) for n in (n0, n1)]
+        targets = rng.uniform(0, 1, (m, 2))
+    targets[1] = coords[0][3]
+    return coords, [rng.standard_normal(n0), rng.standard_normal(n1)], targets
+
+
+@pytest.mark.parametrize("metric,params,tile,lookahead", [(0, HALF, 128, True), (1, GENERIC_KM, 256, True), (0, HALF, 256, False)])
+def test_block_cyclic_single_rank_vs_oracle(metric, params, tile, lookahead):
+    from cokrig_b200 import parallel
+    coords, z, targets = _inputs(metric, 700, 650, 420, 17)
+    solver = parallel.BlockCyclicCokriging(parallel.ProcessGrid(1, 1), tile=tile, lookahead=lookahead)
+    for i_pred in (0, 1):
+        pred, var, info = solver.solve(coords, z, targets, params, 2, i_pred, metric)
+        rp, re, _ = orc.joint_predict(orc.Params(params), i_pred, coords, z, targets, "haversine" if metric else "euclidean")
+        assert info == 0
+        assert relerr(pred, rp) < 1e-9
+        assert np.max(np.abs(var - re ** 2)) < 1e-9
+    sigma = orc.joint_cov(orc.Params(params), coords, "haversine" if metric else "euclidean")
+    assert abs(solver.logdet() / np.linalg.slogdet(sigma)[1] - 1) < 1e-10
+
+
+def test_block_cyclic_single_rank_reports_non_pd():
+    from cokrig_b200 import parallel
+    coords, z, targets = _inputs(0, 300, 280, 20, 2)
+    bad = [1, 1, 1.5, 1.5, 1.5, .2, .2, .2, .0, .0, -1.3]
+    _, _, info = parallel.BlockCyclicCokriging(parallel.ProcessGrid(1, 1), tile=128).solve(coords, z, targets, bad, 2, 0, 0)
+    assert info > 0
+
+
+def test_gemm_nt_entry_point_vs_torch():
+    import torch
+    from cokrig_b200 import ops
+    from cokrig_b200._lib import check, lib
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for (m, n, k) in ((257, 130, 96), (128, 128, 128), (1, 5, 3), (300, 64, 513)):
+        a = torch.randn(m, k, dtype=torch.float64, device="cuda", generator=g)
+        b = torch.randn(n, k, dtype=torch.float64, device="cuda", generator=g)
+        c = torch.randn(m, n, dtype=torch.float64, device="cuda", generator=g)
+        ref = c - a @ b.T
+        check(lib.ck_gemm_nt(ops._ptr(a), k, ops._ptr(b), k, ops._ptr(c), n, m, n, k, 1, ops._stream()))
+        assert (c - ref).abs().max().item() < 1e-11 * k
+        check(lib.ck_gemm_nt(ops._ptr(a), k, ops._ptr(b), k, ops._ptr(c), n, m, n, k, 0, ops._stream()))
+        assert (c - a @ b.T).abs().max().item() < 1e-11 * k
+
+
+def test_two_gpus_under_torchrun():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (run tools/mg_check.py under torchrun on a multi-GPU box)")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(ROOT, "tools", "mg_check.py"), "--n", "3000", "--m", "1000", "--tile", "512"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
