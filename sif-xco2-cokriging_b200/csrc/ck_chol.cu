@@ -59,8 +59,11 @@ struct GemmArgs {
 };
 
 // CTA tile (32*WM) x (32*WN); each of the 8 warps owns a 32 x 32 sub-tile = 4 x 4 DMMA tiles.
-template <int WM, int WN, bool VEC16>
+// VEC16: operands 16-byte aligned with even leading dimensions (vector copies / stores); KFULL: additionally
+// K % G_BK == 0, so every k-tile is full and the branch-free fast loader is used throughout.
+template <int WM, int WN, bool VEC16, bool KFULL>
 __global__ void __launch_bounds__(G_THREADS, 2) ck_gemm_nt_kernel(GemmArgs g) {
+  static_assert(VEC16 || !KFULL, "KFULL needs VEC16");
   constexpr int BM = 32 * WM, BN = 32 * WN;
   constexpr int STAGE_ELEMS = (BM + BN) * G_LDS;
   extern __shared__ __align__(16) double smem[];
@@ -96,45 +99,82 @@ __global__ void __launch_bounds__(G_THREADS, 2) ck_gemm_nt_kernel(GemmArgs g) {
   const int wm = warp / WN, wn = warp % WN;
   const int g4 = lane >> 2, t4 = lane & 3;
 
-  auto load_stage = [&](int stage, long long k0) {
+  // Operand staging.  Fast path (16-byte aligned operands, full k-tile): every thread owns the same 16-byte
+  // column chunk `lch` of rows lrow + 32 i of the A tile (i < BM/32) and of the B tile (i < BN/32).  All index
+  // arithmetic is done ONCE here; per stage a thread bumps two running pointers and issues its copies, so the
+  // non-DMMA phase between the barrier and the first DMMA of a stage is a few dozen instructions.  (The two
+  // co-resident CTAs share the DMMA pipe fairly and therefore phase-lock: the pipe idles for the length of
+  // that phase every stage -- 83 % pipe-active with per-stage index math, profiles/r01b_gemm_*.)
+  // Rows past M / N are simply not copied: whatever the buffer holds there only reaches accumulators of C
+  // rows / columns that are never stored.  A partial last k-tile (K % 16 != 0) and unaligned operands take
+  // the element-wise zero-filling path.
+  constexpr int CH = G_BK / 2;                    // 16-byte chunks per row
+  constexpr int RPI = G_THREADS / CH;             // rows covered per pass (32)
+  constexpr int NA = BM / RPI, NB = BN / RPI;     // copies per thread per stage (A, B)
+  static_assert(G_THREADS % CH == 0 && BM % RPI == 0 && BN % RPI == 0, "loader shape");
+  const int lrow = tid / CH, lch = tid % CH;
+  const double* pa = g.A + (m0 + lrow) * g.lda + lch * 2;  // running pointers: advanced by G_BK per issued stage
+  const double* pb = g.B + (n0 + lrow) * g.ldb + lch * 2;
+  const long long sa = (long long)RPI * g.lda, sb = (long long)RPI * g.ldb;
+  unsigned vmask = 0;  // bit i: A row valid (i < NA); bit NA + i: B row valid
+#pragma unroll
+  for (int i = 0; i < NA; ++i) vmask |= (m0 + lrow + i * RPI < g.M) ? (1u << i) : 0u;
+#pragma unroll
+  for (int i = 0; i < NB; ++i) vmask |= (n0 + lrow + i * RPI < g.N) ? (1u << (NA + i)) : 0u;
+  const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
+  const unsigned sdst0 = sbase + (unsigned)((lrow * G_LDS + lch * 2) * (int)sizeof(double));
+  constexpr unsigned STAGE_BYTES = (unsigned)(STAGE_ELEMS * sizeof(double));
+
+  // fast loader: `on` = 0 turns every copy off (past the last k-tile); no branches
+  auto load_fast = [&](int stage, unsigned on) {
+    const unsigned dst = sdst0 + (unsigned)stage * STAGE_BYTES;
+    const unsigned vm = on ? vmask : 0u;
+    const double* qa = pa;
+    const double* qb = pb;
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+      asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %2, 0;\n @p cp.async.cg.shared.global [%0], [%1], 16;\n}\n" ::"r"(
+                       dst + (unsigned)(i * RPI * G_LDS * (int)sizeof(double))),
+                   "l"(qa), "r"(vm & (1u << i)));
+      qa += sa;
+    }
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+      asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %2, 0;\n @p cp.async.cg.shared.global [%0], [%1], 16;\n}\n" ::"r"(
+                       dst + (unsigned)((BM + i * RPI) * G_LDS * (int)sizeof(double))),
+                   "l"(qb), "r"(vm & (1u << (NA + i))));
+      qb += sb;
+    }
+    pa += G_BK;
+    pb += G_BK;
+  };
+  // generic loader: element-wise, zero-fills rows past M / N and the k-tail
+  auto load_slow = [&](int stage, long long k0) {
     double* base = smem + stage * STAGE_ELEMS;
-    if (VEC16) {
-      constexpr int CH = G_BK / 2;  // 16-byte chunks per row
-#pragma unroll
-      for (int idx = tid; idx < (BM + BN) * CH; idx += G_THREADS) {
-        const int row = idx / CH, ch = idx % CH;
-        const long long gk = k0 + ch * 2;
-        const bool isA = row < BM;
-        const long long gr = isA ? m0 + row : n0 + (row - BM);
-        const long long lim = isA ? g.M : g.N;
-        long long rem = (g.K - gk) * 8;
-        int bytes = (gr < lim && rem > 0) ? (rem >= 16 ? 16 : (int)rem) : 0;
-        const double* src = (isA ? g.A + (bytes ? gr * g.lda : 0) : g.B + (bytes ? gr * g.ldb : 0)) + (bytes ? gk : 0);
-        cp_async16(base + row * G_LDS + ch * 2, src, bytes);
-      }
-    } else {
-#pragma unroll
-      for (int idx = tid; idx < (BM + BN) * G_BK; idx += G_THREADS) {
-        const int row = idx / G_BK, ch = idx % G_BK;
-        const long long gk = k0 + ch;
-        const bool isA = row < BM;
-        const long long gr = isA ? m0 + row : n0 + (row - BM);
-        const long long lim = isA ? g.M : g.N;
-        const int bytes = (gr < lim && gk < g.K) ? 8 : 0;
-        const double* src = (isA ? g.A + (bytes ? gr * g.lda : 0) : g.B + (bytes ? gr * g.ldb : 0)) + (bytes ? gk : 0);
-        cp_async8(base + row * G_LDS + ch, src, bytes);
-      }
+#pragma unroll 1
+    for (int idx = tid; idx < (BM + BN) * G_BK; idx += G_THREADS) {
+      const int row = idx / G_BK, ch = idx % G_BK;
+      const long long gk = k0 + ch;
+      const bool isA = row < BM;
+      const long long gr = isA ? m0 + row : n0 + (row - BM);
+      const long long lim = isA ? g.M : g.N;
+      const int bytes = (gr < lim && gk < g.K) ? 8 : 0;
+      const double* src = (isA ? g.A + (bytes ? gr * g.lda : 0) : g.B + (bytes ? gr * g.ldb : 0)) + (bytes ? gk : 0);
+      cp_async8(base + row * G_LDS + ch, src, bytes);
     }
   };
 
   const long long KT = (g.K + G_BK - 1) / G_BK;
 #pragma unroll
   for (int s = 0; s < G_STAGES - 1; ++s) {
-    if (s < KT) load_stage(s, (long long)s * G_BK);
+    if (KFULL) load_fast(s, s < KT ? 1u : 0u);
+    else if (s < KT) load_slow(s, (long long)s * G_BK);
     cp_async_commit();
   }
 
-  // accumulators: acc[mi][ni][0..1] = C[m0 + wm*32 + mi*8 + g4][n0 + wn*32 + ni*8 + 2*t4 + {0,1}]
+  // accumulators: acc[mi][ni][0..1] <-> C[m0 + wm*32 + mi*8 + g4][n0 + wn*32 + ni*8 + 2*t4 + {0,1}]
+  // mode 1 accumulates  acc = -C + A B^T  and stores -acc: bitwise equal to C - A B^T (negation is exact and
+  // round-to-nearest is sign-symmetric) without touching the operand fragments in the main loop.
   double acc[4][4][2];
   const long long crow0 = m0 + wm * 32 + g4, ccol0 = n0 + wn * 32 + 2 * t4;
 #pragma unroll
@@ -149,44 +189,57 @@ __global__ void __launch_bounds__(G_THREADS, 2) ck_gemm_nt_kernel(GemmArgs g) {
           const double* p = g.C + r * g.ldc + c;
           if (VEC16 && c + 1 < g.N) {
             const double2 v = *reinterpret_cast<const double2*>(p);
-            acc[mi][ni][0] = v.x;
-            acc[mi][ni][1] = v.y;
+            acc[mi][ni][0] = -v.x;
+            acc[mi][ni][1] = -v.y;
           } else {
-            if (c < g.N) acc[mi][ni][0] = p[0];
-            if (c + 1 < g.N) acc[mi][ni][1] = p[1];
+            if (c < g.N) acc[mi][ni][0] = -p[0];
+            if (c + 1 < g.N) acc[mi][ni][1] = -p[1];
           }
         }
       }
     }
-  const unsigned long long sign = (g.mode == 1) ? 0x8000000000000000ULL : 0ULL;
 
+  const unsigned a_off = (unsigned)(((wm * 32 + g4) * G_LDS + t4) * (int)sizeof(double));
+  const unsigned b_off = (unsigned)(((BM + wn * 32 + g4) * G_LDS + t4) * (int)sizeof(double));
+  const char* sm_c = reinterpret_cast<const char*>(smem);
+  auto mma_step = [&](const double* As, const double* Bs, int kk) {
+    double a[4], b[4];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) a[mi] = As[mi * 8 * G_LDS + kk];
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) b[ni] = Bs[ni * 8 * G_LDS + kk];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+  };
+  int rd = 0, wr = G_STAGES - 1;
   for (long long kt = 0; kt < KT; ++kt) {
     cp_async_wait<G_STAGES - 2>();
-    __syncthreads();
-    {
-      const long long nk = kt + G_STAGES - 1;
-      if (nk < KT) load_stage((int)(nk % G_STAGES), nk * G_BK);
+    __syncthreads();  // stage `rd` has landed for everybody; everybody is done with stage `wr` (read at kt - 1)
+    const double* As = reinterpret_cast<const double*>(sm_c + (unsigned)rd * STAGE_BYTES + a_off);
+    const double* Bs = reinterpret_cast<const double*>(sm_c + (unsigned)rd * STAGE_BYTES + b_off);
+    const long long nk = kt + G_STAGES - 1;
+    if (KFULL) {
+      // the refill of stage `wr` is issued in the shadow of the first DMMA group, not between the barrier and it
+      mma_step(As, Bs, 0);
+      load_fast(wr, nk < KT ? 1u : 0u);
       cp_async_commit();
+#pragma unroll
+      for (int kk = 4; kk < G_BK; kk += 4) mma_step(As, Bs, kk);
+    } else {
+      if (nk < KT) load_slow(wr, nk * G_BK);
+      cp_async_commit();
+#pragma unroll
+      for (int kk = 0; kk < G_BK; kk += 4) mma_step(As, Bs, kk);
     }
-    const double* As = smem + (int)(kt % G_STAGES) * STAGE_ELEMS + (wm * 32 + g4) * G_LDS + t4;
-    const double* Bs = smem + (int)(kt % G_STAGES) * STAGE_ELEMS + (BM + wn * 32 + g4) * G_LDS + t4;
-#pragma unroll
-    for (int kk = 0; kk < G_BK; kk += 4) {
-      double a[4], b[4];
-#pragma unroll
-      for (int mi = 0; mi < 4; ++mi)
-        a[mi] = __longlong_as_double(__double_as_longlong(As[mi * 8 * G_LDS + kk]) ^ sign);
-#pragma unroll
-      for (int ni = 0; ni < 4; ++ni) b[ni] = Bs[ni * 8 * G_LDS + kk];
-#pragma unroll
-      for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-        for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
-    }
+    rd = (rd + 1 == G_STAGES) ? 0 : rd + 1;
+    wr = (wr + 1 == G_STAGES) ? 0 : wr + 1;
   }
   cp_async_wait<0>();
   __syncthreads();  // all operand reads of this CTA are complete before any store (in-place TRSM safety)
 
+  const double sgn = (g.mode == 1) ? -1.0 : 1.0;
 #pragma unroll
   for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
@@ -196,11 +249,12 @@ __global__ void __launch_bounds__(G_THREADS, 2) ck_gemm_nt_kernel(GemmArgs g) {
       double* p = g.C + r * g.ldc + c;
       const bool ok0 = c < g.N && (!masked || c - coff <= r - roff);
       const bool ok1 = c + 1 < g.N && (!masked || c + 1 - coff <= r - roff);
+      const double v0 = sgn * acc[mi][ni][0], v1 = sgn * acc[mi][ni][1];
       if (VEC16 && ok0 && ok1) {
-        *reinterpret_cast<double2*>(p) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+        *reinterpret_cast<double2*>(p) = make_double2(v0, v1);
       } else {
-        if (ok0) p[0] = acc[mi][ni][0];
-        if (ok1) p[1] = acc[mi][ni][1];
+        if (ok0) p[0] = v0;
+        if (ok1) p[1] = v1;
       }
     }
 }
@@ -211,10 +265,12 @@ static int gemm_launch(const GemmArgs& g, cudaStream_t st) {
   constexpr size_t SMEM = (size_t)G_STAGES * (BM + BN) * G_LDS * sizeof(double);
   if (g.M <= 0 || g.N <= 0) return CK_OK;
   const bool vec = ((((uintptr_t)g.A | (uintptr_t)g.B | (uintptr_t)g.C) & 15) == 0) && !((g.lda | g.ldb | g.ldc) & 1);
+  const bool kfull = vec && (g.K % G_BK == 0);
   static bool attr_done = false;
   if (!attr_done) {
-    CK_CUDA(cudaFuncSetAttribute(ck_gemm_nt_kernel<WM, WN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-    CK_CUDA(cudaFuncSetAttribute(ck_gemm_nt_kernel<WM, WN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    CK_CUDA(cudaFuncSetAttribute(ck_gemm_nt_kernel<WM, WN, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    CK_CUDA(cudaFuncSetAttribute(ck_gemm_nt_kernel<WM, WN, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    CK_CUDA(cudaFuncSetAttribute(ck_gemm_nt_kernel<WM, WN, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     attr_done = true;
   }
   const long long tm = (g.M + BM - 1) / BM, tn = (g.N + BN - 1) / BN;
@@ -229,8 +285,9 @@ static int gemm_launch(const GemmArgs& g, cudaStream_t st) {
     CK_REQUIRE(tm <= 65535, "too many row tiles");
     grid = dim3((unsigned)tn, (unsigned)tm, 1);
   }
-  if (vec) ck_gemm_nt_kernel<WM, WN, true><<<grid, G_THREADS, SMEM, st>>>(g);
-  else ck_gemm_nt_kernel<WM, WN, false><<<grid, G_THREADS, SMEM, st>>>(g);
+  if (kfull) ck_gemm_nt_kernel<WM, WN, true, true><<<grid, G_THREADS, SMEM, st>>>(g);
+  else if (vec) ck_gemm_nt_kernel<WM, WN, true, false><<<grid, G_THREADS, SMEM, st>>>(g);
+  else ck_gemm_nt_kernel<WM, WN, false, false><<<grid, G_THREADS, SMEM, st>>>(g);
   CK_LAUNCH_CHECK();
   return CK_OK;
 }
@@ -491,6 +548,47 @@ static int factor_range(const CholCtx& c, ck_i64 b0, ck_i64 b1) {
   return CK_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Look-ahead.  The panel chain of an aggregate (4 x [potf2 -> panel TRSM] + thin updates) is a serial
+// sequence of small, latency-bound launches (~0.6 ms per aggregate) during which most SMs idle.  With
+// look-ahead the trailing update of aggregate j is split into (a) the columns of aggregate j+1 and
+// (b) the rest; the panel chain of aggregate j+1 then runs on an internal high-priority stream
+// concurrently with (b).  Every entry still receives the same K-ordered sum, so results are bitwise
+// identical with and without look-ahead.  CK_LOOKAHEAD=0 disables it.
+// ------------------------------------------------------------------------------------------------
+#include <mutex>
+struct SideStream {
+  cudaStream_t s = nullptr;
+  cudaEvent_t ev_a = nullptr, ev_c = nullptr;
+  std::mutex enqueue;  // host threads enqueueing on the same device take turns (the events are shared)
+};
+static int lookahead_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CK_LOOKAHEAD");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v;
+}
+static int side_stream(SideStream** out) {
+  static SideStream table[64];
+  static std::mutex mu;
+  int dev = 0;
+  CK_CUDA(cudaGetDevice(&dev));
+  CK_REQUIRE(dev >= 0 && dev < 64, "device index %d out of range", dev);
+  std::lock_guard<std::mutex> lock(mu);
+  SideStream& t = table[dev];
+  if (!t.s) {
+    int lo = 0, hi = 0;
+    CK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CK_CUDA(cudaStreamCreateWithPriority(&t.s, cudaStreamNonBlocking, hi));
+    CK_CUDA(cudaEventCreateWithFlags(&t.ev_a, cudaEventDisableTiming));
+    CK_CUDA(cudaEventCreateWithFlags(&t.ev_c, cudaEventDisableTiming));
+  }
+  *out = &t;
+  return CK_OK;
+}
+
 extern "C" int ck_potrf(double* a, ck_i64 n, ck_i64 ld, void* ws, int* info, void* stream) {
   CK_REQUIRE(n >= 0, "negative size");
   CK_REQUIRE(info, "info is NULL");
@@ -503,17 +601,44 @@ extern "C" int ck_potrf(double* a, ck_i64 n, ck_i64 ld, void* ws, int* info, voi
   const ck_i64 nblk = (n + CK_NB - 1) / CK_NB;
   const int agg = agg_blocks();
   int rc;
+  SideStream* side = nullptr;
+  if (lookahead_enabled() && nblk > 2 * agg) {
+    if ((rc = side_stream(&side))) return rc;
+  }
+  std::unique_lock<std::mutex> turn;
+  if (side) turn = std::unique_lock<std::mutex>(side->enqueue);
+  CholCtx cs = c;
+  if (side) cs.st = side->s;
+  if ((rc = factor_range(c, 0, agg < nblk ? agg : nblk))) return rc;
   for (ck_i64 b0 = 0; b0 < nblk; b0 += agg) {
     const ck_i64 b1 = b0 + agg < nblk ? b0 + agg : nblk;
-    if ((rc = factor_range(c, b0, b1))) return rc;
     const ck_i64 k0 = c.s(b0), k1 = c.s(b1);
-    if (k1 < n) {
-      GemmArgs s;  // trailing: A[k1:, k1:] -= P P^T with P = A[k1:, k0:k1], lower tiles, K = 128 * agg
-      s.A = a + k1 * ld + k0; s.lda = ld;
-      s.B = a + k1 * ld + k0; s.ldb = ld;
-      s.C = a + k1 * ld + k1; s.ldc = ld;
-      s.M = n - k1; s.N = n - k1; s.K = k1 - k0; s.mode = 1; s.lower_only = 1;
+    if (k1 >= n) break;
+    const ck_i64 b2 = b1 + agg < nblk ? b1 + agg : nblk;
+    const ck_i64 k2 = c.s(b2);
+    {
+      GemmArgs u;  // (a) columns of the next aggregate: A[k1:, k1:k2] -= P P[k1:k2]^T, P = A[k1:, k0:k1]
+      u.A = a + k1 * ld + k0; u.lda = ld;
+      u.B = a + k1 * ld + k0; u.ldb = ld;
+      u.C = a + k1 * ld + k1; u.ldc = ld;
+      u.M = n - k1; u.N = k2 - k1; u.K = k1 - k0; u.mode = 1; u.lower_only = 2;
+      if ((rc = gemm_launch<4, 2>(u, st))) return rc;
+    }
+    GemmArgs s;  // (b) the rest: A[k2:, k2:] -= P P^T with P = A[k2:, k0:k1], lower tiles, K = 128 * agg
+    s.A = a + k2 * ld + k0; s.lda = ld;
+    s.B = a + k2 * ld + k0; s.ldb = ld;
+    s.C = a + k2 * ld + k2; s.ldc = ld;
+    s.M = n - k2; s.N = n - k2; s.K = k1 - k0; s.mode = 1; s.lower_only = 1;
+    if (side && k2 < n) {
+      CK_CUDA(cudaEventRecord(side->ev_a, st));
+      CK_CUDA(cudaStreamWaitEvent(side->s, side->ev_a, 0));
+      if ((rc = factor_range(cs, b1, b2))) return rc;  // panel chain of the next aggregate, concurrently with (b)
+      CK_CUDA(cudaEventRecord(side->ev_c, side->s));
       if ((rc = gemm_launch<4, 2>(s, st))) return rc;
+      CK_CUDA(cudaStreamWaitEvent(st, side->ev_c, 0));
+    } else {
+      if (k2 < n && (rc = gemm_launch<4, 2>(s, st))) return rc;
+      if ((rc = factor_range(c, b1, b2))) return rc;
     }
   }
   return CK_OK;
@@ -558,21 +683,49 @@ extern "C" int ck_trsm_lower(const double* l, ck_i64 n, ck_i64 ld, const void* w
   if (n == 0 || nrhs == 0) return CK_OK;
   CK_REQUIRE(l && ws && rhs, "null pointer");
   CK_REQUIRE(ld >= n && ld_rhs >= n, "leading dimension too small");
-  TrsmCtx c{l, n, ld, static_cast<const double*>(ws), rhs, nrhs, ld_rhs, ck_stream(stream)};
+  cudaStream_t st = ck_stream(stream);
+  TrsmCtx c{l, n, ld, static_cast<const double*>(ws), rhs, nrhs, ld_rhs, st};
   const ck_i64 nblk = (n + CK_NB - 1) / CK_NB;
   const int agg = agg_blocks();
   int rc;
+  SideStream* side = nullptr;
+  if (lookahead_enabled() && nblk > 2 * agg && nrhs >= 1024) {
+    if ((rc = side_stream(&side))) return rc;
+  }
+  std::unique_lock<std::mutex> turn;
+  if (side) turn = std::unique_lock<std::mutex>(side->enqueue);
+  TrsmCtx cs = c;
+  if (side) cs.st = side->s;
+  if ((rc = solve_range(c, 0, agg < nblk ? agg : nblk))) return rc;
   for (ck_i64 b0 = 0; b0 < nblk; b0 += agg) {
     const ck_i64 b1 = b0 + agg < nblk ? b0 + agg : nblk;
-    if ((rc = solve_range(c, b0, b1))) return rc;
     const ck_i64 k0 = c.s(b0), k1 = c.s(b1);
-    if (k1 < n) {
-      GemmArgs u;  // R[:, k1:] -= V[:, k0:k1] L[k1:, k0:k1]^T, K = 128 * agg
+    if (k1 >= n) break;
+    const ck_i64 b2 = b1 + agg < nblk ? b1 + agg : nblk;
+    const ck_i64 k2 = c.s(b2);
+    {
+      GemmArgs u;  // (a) columns of the next aggregate: R[:, k1:k2] -= V[:, k0:k1] L[k1:k2, k0:k1]^T
       u.A = rhs + k0; u.lda = ld_rhs;
       u.B = l + k1 * ld + k0; u.ldb = ld;
       u.C = rhs + k1; u.ldc = ld_rhs;
-      u.M = nrhs; u.N = n - k1; u.K = k1 - k0; u.mode = 1; u.lower_only = 0;
-      if ((rc = gemm_launch<4, 2>(u, c.st))) return rc;
+      u.M = nrhs; u.N = k2 - k1; u.K = k1 - k0; u.mode = 1; u.lower_only = 0;
+      if ((rc = gemm_launch<4, 2>(u, st))) return rc;
+    }
+    GemmArgs r;  // (b) the rest: R[:, k2:] -= V[:, k0:k1] L[k2:, k0:k1]^T, K = 128 * agg
+    r.A = rhs + k0; r.lda = ld_rhs;
+    r.B = l + k2 * ld + k0; r.ldb = ld;
+    r.C = rhs + k2; r.ldc = ld_rhs;
+    r.M = nrhs; r.N = n - k2; r.K = k1 - k0; r.mode = 1; r.lower_only = 0;
+    if (side && k2 < n) {
+      CK_CUDA(cudaEventRecord(side->ev_a, st));
+      CK_CUDA(cudaStreamWaitEvent(side->s, side->ev_a, 0));
+      if ((rc = solve_range(cs, b1, b2))) return rc;  // small solves of the next aggregate, concurrently with (b)
+      CK_CUDA(cudaEventRecord(side->ev_c, side->s));
+      if ((rc = gemm_launch<4, 2>(r, st))) return rc;
+      CK_CUDA(cudaStreamWaitEvent(st, side->ev_c, 0));
+    } else {
+      if (k2 < n && (rc = gemm_launch<4, 2>(r, st))) return rc;
+      if ((rc = solve_range(c, b1, b2))) return rc;
     }
   }
   return CK_OK;

@@ -39,7 +39,12 @@ def test_block_cyclic_single_rank_vs_oracle(metric, params, tile, lookahead):
         pred, var, info = solver.solve(coords, z, targets, params, 2, i_pred, metric)
         rp, re, _ = orc.joint_predict(orc.Params(params), i_pred, coords, z, targets, "haversine" if metric else "euclidean")
         assert info == 0
-        assert relerr(pred, rp) < 1e-9
+        # predictions cross zero on this random field (values down to 1e-3 of the field scale) while the solve
+        # error is normwise (kappa(Sigma) ~ 1e4-1e5): compare relative to the field scale, and pointwise
+        # relative where the prediction is not small
+        assert np.max(np.abs(pred - rp)) / np.max(np.abs(rp)) < 1e-9
+        big = np.abs(rp) > 0.1 * np.max(np.abs(rp))
+        assert relerr(pred[big], rp[big]) < 1e-9
         assert np.max(np.abs(var - re ** 2)) < 1e-9
     sigma = orc.joint_cov(orc.Params(params), coords, "haversine" if metric else "euclidean")
     assert abs(solver.logdet() / np.linalg.slogdet(sigma)[1] - 1) < 1e-10
