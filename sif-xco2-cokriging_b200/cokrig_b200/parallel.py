@@ -304,9 +304,11 @@ class BlockCyclicCokriging:
         ev = {"t0": self._mark()}
         K.assemble(coords_d, t_d, z_d, params, n_procs, i_pred, metric, tb, g, local)
         ev["t1"] = self._mark()
+        with K.stream("main"):
+            assembled = K.event()  # the panel stream must not touch `local` before the assembly kernels are done
 
         main_done = [None, None]  # main_done[b]: last trailing update that read stage[b] has finished
-        panel_ready = self._factor_panel(0, local, stage[0], packs[0], info, None, None) if TC else None
+        panel_ready = self._factor_panel(0, local, stage[0], packs[0], info, None, assembled) if TC else None
         for k in range(TC):
             buf = k % 2
             nxt = None

@@ -503,7 +503,7 @@ static int agg_blocks() {
   static int v = 0;
   if (v == 0) {
     const char* e = getenv("CK_AGG_BLOCKS");
-    v = e ? atoi(e) : 4;
+    v = e ? atoi(e) : 8;
     if (v < 1) v = 1;
     if (v > 64) v = 64;
   }
