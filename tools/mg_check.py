@@ -1,7 +1,7 @@
 """Multi-GPU check (one process per GPU; run under torchrun on a box with >= 2 B200s):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 \
-        tools/mg_check.py [--n 20000 --m 8833 --tile 1024] [--out gpurun_out/mg_check.json]
+        tools/mg_check.py [--points 20000 --targets 8833 --tile 1024] [--out gpurun_out/mg_check.json]
 
 1. K2: the row-block sharded variogram gives the SAME BITS (counts and FP64 sums) as the single-GPU call.
 2. C5 path: BlockCyclicCokriging on the P x Q grid vs the single-GPU path (ck_potrf + ck_potrs_predict) and,
@@ -29,8 +29,8 @@ PARAMS = [1.0, 0.8, 1.5, 1.5, 1.5, 500.0, 500.0, 500.0, 0.02, 0.02, -0.2]
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=6000, help="points per variable of the timed block-cyclic solve")
-    ap.add_argument("--m", type=int, default=2000)
+    ap.add_argument("--points", type=int, default=6000, help="points per variable of the timed block-cyclic solve")
+    ap.add_argument("--targets", type=int, default=2000)
     ap.add_argument("--tile", type=int, default=1024)
     ap.add_argument("--grid", default="", help="PxQ (default: as square as possible)")
     ap.add_argument("--steps", type=int, default=2)
@@ -95,8 +95,8 @@ def main():
     torch.cuda.empty_cache()
 
     # ---- 3. timed solve at the requested size
-    coords, z, targets = make_workload(args.n, args.m, seed=0)
-    N = 2 * args.n
+    coords, z, targets = make_workload(args.points, args.targets, seed=0)
+    N = 2 * args.points
     solver = parallel.BlockCyclicCokriging(grid, tile=args.tile)
     report["local_GB"] = solver.local_bytes(N, len(targets)) / 1e9
     times = []
