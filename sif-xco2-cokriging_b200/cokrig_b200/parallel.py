@@ -376,6 +376,30 @@ class BlockCyclicCokriging:
             dist.all_reduce(s)
         return float(s.item())
 
+    def gather_factor_rows(self, rows: Sequence[int]) -> np.ndarray:
+        """Rows `rows` (stacked data indices) of the lower Cholesky factor L, assembled from the ranks that
+        hold their tiles (after solve()); zeros right of the diagonal.  Every rank gets the same array.
+        For sampled checks of L L^T against Sigma at sizes where nothing else can hold the matrix."""
+        local, _ = self._keep
+        g, tb = self.g, self.tb
+        rows = [int(r) for r in rows]
+        out = self.k.zeros(len(rows), self.TC * tb)
+        for a, r in enumerate(rows):
+            I, off = divmod(r, tb)
+            if I % g.P != g.p:
+                continue
+            li = I // g.P
+            for lj in range(self.LCt):
+                J = lj * g.Q + g.q
+                if J > I:
+                    break
+                out[a, J * tb:(J + 1) * tb] = local[li * tb + off, lj * tb:(lj + 1) * tb]
+            if I % g.Q == g.q:  # diagonal tile: only columns <= off are part of L
+                out[a, I * tb + off + 1:(I + 1) * tb] = 0.0
+        if g.world > 1:
+            dist.all_reduce(out)
+        return out[:, : self.N].cpu().numpy()
+
     # -- pieces -----------------------------------------------------------------------------------
     def _factor_panel(self, k: int, local, stage_b, pack, info, pending, stage_free):
         """Panel stream: [apply `pending` = (k-1, its stage, its ready event) to column k on its owners] ->

@@ -78,7 +78,10 @@ def _block_cyclic(rank, world, P, Q, tile, n0, n1, m, params, n_procs, i_pred, m
     grid = parallel.ProcessGrid(P, Q)
     solver = parallel.BlockCyclicCokriging(grid, tile=tile, kernels=NumpyKernels(), lookahead=lookahead)
     pred, var, info = solver.solve(coords, z, targets, params, n_procs, i_pred, metric)
+    n_all = sum(len(c) for c in coords)
+    rows = [0, 1, min(130, n_all - 1), n_all // 2, n_all - 1]
     return {"pred": pred, "var": var, "info": info, "logdet": solver.logdet(), "coords": coords, "z": z,
+            "rows": rows, "L_rows": solver.gather_factor_rows(rows),
             "targets": targets, "local_bytes": solver.local_bytes(sum(len(c) for c in coords), m)}
 
 

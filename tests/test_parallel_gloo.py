@@ -24,6 +24,9 @@ def _check_against_oracle(res, params, n_procs, i_pred, metric):
     assert np.max(np.abs(r0["pred"] - pred) / np.maximum(np.abs(pred), 1e-300)) < 1e-9
     assert np.max(np.abs(r0["var"] - err ** 2)) < 1e-9 * (params[i_pred if n_procs == 2 else 0] ** 2)
     sigma = orc.joint_cov(P, r0["coords"], name)
+    L = np.linalg.cholesky(sigma)
+    for r in res:  # rows of the factor gathered from their owners
+        assert np.max(np.abs(r["L_rows"] - L[r["rows"]])) < 1e-12
     assert abs(r0["logdet"] - np.linalg.slogdet(sigma)[1]) < 1e-9 * abs(np.linalg.slogdet(sigma)[1]) + 1e-9
 
 

@@ -35,6 +35,10 @@ def main():
     ap.add_argument("--grid", default="", help="PxQ (default: as square as possible)")
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--skip-single", action="store_true", help="do not run the single-GPU comparison at the timed size")
+    ap.add_argument("--workload", default="c3", choices=["c3", "c5"],
+                    help="c3: bench.py's CONUS workload; c5: 1 degree global lattice, 64 800 cells per variable (co-located), "
+                         "targets = random cells, nugget 0.05 (BASELINE config 5; --points is ignored)")
+    ap.add_argument("--sample-rows", type=int, default=12, help="rows of L gathered for the sampled L L^T check")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
 
@@ -95,7 +99,17 @@ def main():
     torch.cuda.empty_cache()
 
     # ---- 3. timed solve at the requested size
-    coords, z, targets = make_workload(args.points, args.targets, seed=0)
+    params = list(PARAMS)
+    if args.workload == "c5":
+        glat, glon = -89.5 + np.arange(180.0), -179.5 + np.arange(360.0)
+        cells = np.ascontiguousarray(np.array([(a, o) for a in glat for o in glon]))
+        coords = [cells, cells.copy()]
+        z = [np.random.default_rng(50 + k).standard_normal(len(cells)) for k in range(2)]
+        targets = cells[np.sort(np.random.default_rng(7).choice(len(cells), args.targets, replace=False))]
+        params[8] = params[9] = 0.05
+        args.points = len(cells)
+    else:
+        coords, z, targets = make_workload(args.points, args.targets, seed=0)
     N = 2 * args.points
     solver = parallel.BlockCyclicCokriging(grid, tile=args.tile)
     report["local_GB"] = solver.local_bytes(N, len(targets)) / 1e9
@@ -106,7 +120,7 @@ def main():
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        pred, var, info = solver.solve(coords, z, targets, PARAMS, 2, 0, METRIC_HAVERSINE)
+        pred, var, info = solver.solve(coords, z, targets, params, 2, 0, METRIC_HAVERSINE)
         e1.record()
         torch.cuda.synchronize()
         t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
@@ -115,17 +129,38 @@ def main():
         times.append(float(t.item()))
         phases = dict(solver.timings)
     flops = N ** 3 / 3.0 + float(N) * N * (len(targets) + 1)
-    report.update({"N": N, "m": len(targets), "tile": args.tile, "grid": f"{P}x{Q}", "solve_ms": times, "info": info,
+    report.update({"workload": args.workload, "N": N, "m": len(targets), "tile": args.tile, "grid": f"{P}x{Q}", "solve_ms": times, "info": info,
                    "phases_ms_rank0": phases, "TFs_aggregate": flops / (min(times) / 1e3) / 1e12,
                    "predictions_per_s": len(targets) / (min(times) / 1e3)})
     ok &= info == 0
+    # sampled reconstruction: rows of L gathered from their owners, (L L^T)[S, S] against Sigma[S, S] from the oracle
+    if args.sample_rows > 0 and info == 0:
+        S = np.sort(np.random.default_rng(11).choice(N, args.sample_rows, replace=False))
+        S[-1] = N - 1
+        Ls = solver.gather_factor_rows(S)
+        if rank == 0:
+            import cokrig_oracle as orc
+            stacked = np.vstack(coords)
+            P_ = orc.Params(params)
+            ref = np.empty((len(S), len(S)))
+            for a, ia in enumerate(S):
+                for b, ib in enumerate(S):
+                    pa_, pb_ = int(ia >= args.points), int(ib >= args.points)
+                    d = orc.distance_matrix(stacked[ia:ia + 1], stacked[ib:ib + 1], fast_dist=True)
+                    ref[a, b] = (orc.covariance(P_, pa_, d) if pa_ == pb_ else orc.cross_covariance(P_, min(pa_, pb_), max(pa_, pb_), d))[0, 0]
+            rec = Ls @ Ls.T
+            report["sampled_LLt_max_abs_err"] = float(np.max(np.abs(rec - ref)))
+            report["sampled_rows"] = [int(v) for v in S]
+            ok &= report["sampled_LLt_max_abs_err"] < 1e-9
+        report["pred_finite"] = bool(np.isfinite(pred).all() and np.isfinite(var).all())
+        report["var_min"], report["var_max"] = float(var.min()), float(var.max())
     if not args.skip_single and rank == 0:
         del solver
         torch.cuda.empty_cache()
         cd = [ops.coords_to_device(c) for c in coords]
-        f = ops.potrf(ops.joint_cov(cd, PARAMS, 2, METRIC_HAVERSINE))
-        p1, v1 = f.predict(ops.cross_cov(cd, ops.coords_to_device(targets), PARAMS, 2, 0, METRIC_HAVERSINE),
-                           ops.to_device(np.hstack(z)), PARAMS[0] ** 2 + PARAMS[8])
+        f = ops.potrf(ops.joint_cov(cd, params, 2, METRIC_HAVERSINE))
+        p1, v1 = f.predict(ops.cross_cov(cd, ops.coords_to_device(targets), params, 2, 0, METRIC_HAVERSINE),
+                           ops.to_device(np.hstack(z)), params[0] ** 2 + params[8])
         p1, v1 = p1.cpu().numpy(), v1.cpu().numpy()
         report["pred_rel_vs_single_gpu"] = float(np.max(np.abs(pred - p1)) / np.max(np.abs(p1)))
         report["var_abs_vs_single_gpu"] = float(np.max(np.abs(var - v1)))
