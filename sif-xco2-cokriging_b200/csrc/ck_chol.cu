@@ -3,7 +3,7 @@
 //
 // Structure (right-looking, panel width CK_NB = 128, matrix row-major, lower triangle):
 //   for each diagonal block k:
-//     ck_potf2_inv_kernel   one CTA, register-resident 128x128 elimination: L_kk in place and
+//     ck_potf2_inv_kernel   one CTA, 32-column panels (warp-level elimination + DMMA updates): L_kk in place and
 //                           X_k = L_kk^{-1} into the workspace (kept for the solves)
 //     ck_gemm_nt_kernel     panel  A[k+1:, k] <- A[k+1:, k] X_k^T                (TRSM as GEMM, in place)
 //     ck_gemm_nt_kernel     trailing A[k+1:, k+1:] -= P P^T on lower tiles only (DSYRK)
@@ -293,125 +293,189 @@ static int gemm_launch(const GemmArgs& g, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Diagonal block: Cholesky + inverse of the factor, one CTA of 1024 threads, elements in registers.
-// Thread (tx, ty) owns A[ty + 32a][tx + 32b], a, b in 0..3 (2-D cyclic -> balanced as columns retire).
-// Phase 1 (LDL^T-style elimination, one barrier per column): publish column j, every thread applies
-//   A[i][k] -= A[i][j] A[k][j] / d_j to its lower-triangle elements; L[i][j] = A[i][j] / sqrt(d_j).
-// Phase 2 (forward substitution on the identity, one barrier per row): X = L^{-1}.
+// Diagonal block: L_kk = chol(A_kk) and X_k = L_kk^{-1} (128 x 128), one CTA of 512 threads, the block in
+// shared memory.  The elimination is blocked in 32-column panels so that the latency-bound part (one
+// dependent pivot per column) runs inside ONE warp with register-resident rows and warp shuffles --
+// no CTA barrier per column -- and everything else is FP64 DMMA on shared-memory operands:
+//   per 32-panel jb:  warp 0   D = L_d L_d^T by LDL^T-style elimination (lane = row; only 1/d on the critical
+//                              path, sqrt off it), then X_d = L_d^{-1} by forward substitution (lane = column)
+//                     all      panel  P = A[below, jb] X_d^T          (DMMA, row-tile per warp, in place)
+//                     all      trailing A[below, below] -= P P^T       (DMMA, lower 8x8 tiles)
+//   finally the off-diagonal blocks of the inverse, X_ij = -X_d,i (sum_k L_ik X_kj), by DMMA, held in the
+//   (otherwise unused) upper-triangle blocks of the shared-memory matrix.
 // Rows/cols >= nb are padded with the identity so partial blocks need no special cases.
+// (The previous register-resident variant with one CTA barrier per column took 108 us per block; ncu:
+// profiles/r01b_potf2_ncu_full_summary.txt.)
 // ------------------------------------------------------------------------------------------------
-constexpr int P_SMEM_DOUBLES = CK_NB * CK_NB + 2 * (CK_NB + 8) + 2 * CK_NB;
+constexpr int PB = 32;               // panel width inside the diagonal block
+constexpr int P_LDA = CK_NB + 4;     // smem row stride of the block: % 16 == 4 -> conflict-free DMMA fragment loads
+constexpr int P_LDX = PB + 4;        // row stride of the four diagonal inverse blocks
+constexpr int P_THREADS = 512;
+constexpr int P_SMEM_DOUBLES = CK_NB * P_LDA + (CK_NB / PB) * PB * P_LDX + CK_NB;
 
-__global__ void __launch_bounds__(1024, 1)
+__global__ void __launch_bounds__(P_THREADS, 1)
     ck_potf2_inv_kernel(double* __restrict__ A, long long ld, int nb, double* __restrict__ X, int* info, int k0) {
   extern __shared__ __align__(16) double sm[];
-  double* Lsh = sm;                           // Lsh[j*128 + i] = L[i][j]
-  double* colbuf = Lsh + CK_NB * CK_NB;       // 2 x (128 + 8): published column/row; [128]=1/d, [129]=sqrt d, [130]=1/sqrt d
-  double* rsh = colbuf + 2 * (CK_NB + 8);     // 1/sqrt(d_j) = 1/L[j][j]
-  double* sqh = rsh + CK_NB;                  // sqrt(d_j)
+  double* As = sm;                                   // As[i * P_LDA + k]
+  double* Xd = As + CK_NB * P_LDA;                   // Xd[jb][r * P_LDX + c] = (L_d^{-1})[r][c]
+  double* rsd = Xd + (CK_NB / PB) * PB * P_LDX;      // 1 / L[k][k]
   __shared__ int bad;
-  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g4 = lane >> 2, t4 = lane & 3;
+  constexpr int NW = P_THREADS / 32;
   if (tid == 0) bad = 0;
-  double a[4][4];
-#pragma unroll
-  for (int ai = 0; ai < 4; ++ai)
-#pragma unroll
-    for (int bi = 0; bi < 4; ++bi) {
-      const int i = ty + 32 * ai, k = tx + 32 * bi;
-      double v = (i == k) ? 1.0 : 0.0;
-      if (i < nb && k < nb) v = (k <= i) ? A[(long long)i * ld + k] : 0.0;
-      a[ai][bi] = v;
-    }
-  __syncthreads();
-#pragma unroll
-  for (int bj = 0; bj < 4; ++bj) {
-    for (int tj = 0; tj < 32; ++tj) {
-      const int j = bj * 32 + tj;
-      double* col = colbuf + (j & 1) * (CK_NB + 8);
-      if (tx == tj) {
-#pragma unroll
-        for (int ai = bj; ai < 4; ++ai) col[ty + 32 * ai] = a[ai][bj];
-        if (ty == tj) {  // owner of the pivot
-          const double d = a[bj][bj];
-          const double sq = sqrt(d);
-          col[CK_NB] = 1.0 / d;
-          col[CK_NB + 1] = sq;
-          col[CK_NB + 2] = 1.0 / sq;
-          if (!(d > 0.0) && bad == 0) bad = j + 1;
-        }
-      }
-      __syncthreads();
-      const double invd = col[CK_NB];
-      if (tid < CK_NB) {
-        const double rs = col[CK_NB + 2];
-        Lsh[j * CK_NB + tid] = (tid > j) ? col[tid] * rs : (tid == j ? col[CK_NB + 1] : 0.0);
-        if (tid == 0) {
-          rsh[j] = rs;
-          sqh[j] = col[CK_NB + 1];
-        }
-      }
-#pragma unroll
-      for (int ai = bj; ai < 4; ++ai) {
-        const int i = ty + 32 * ai;
-        if (i > j) {
-          const double li = col[i] * invd;
-#pragma unroll
-          for (int bi = bj; bi <= ai; ++bi) {
-            const int k = tx + 32 * bi;
-            if (k > j && k <= i) a[ai][bi] -= li * col[k];
-          }
-        }
-      }
-    }
+  for (int idx = tid; idx < CK_NB * CK_NB; idx += P_THREADS) {
+    const int i = idx / CK_NB, k = idx % CK_NB;
+    double v = (i == k) ? 1.0 : 0.0;
+    if (i < nb && k < nb) v = (k <= i) ? A[(long long)i * ld + k] : 0.0;
+    As[i * P_LDA + k] = v;
   }
   __syncthreads();
-  // L to global: L[i][k] = a * rs_k (k < i), sqrt(d_k) on the diagonal -- same bits as Lsh
+
+  for (int jb = 0; jb < CK_NB / PB; ++jb) {
+    const int c0 = jb * PB;
+    double* Xdj = Xd + jb * PB * P_LDX;
+    if (warp == 0) {
+      // ---- D = L_d L_d^T, lane = row.  a[k] holds the UNSCALED column entry u_ik until column k is finished.
+      double a[PB];
 #pragma unroll
-  for (int ai = 0; ai < 4; ++ai)
+      for (int k = 0; k < PB; ++k) a[k] = As[(c0 + lane) * P_LDA + c0 + k];
+      int first_bad = 0;
 #pragma unroll
-    for (int bi = 0; bi < 4; ++bi) {
-      const int i = ty + 32 * ai, k = tx + 32 * bi;
-      if (i < nb && k <= i) A[(long long)i * ld + k] = (k == i) ? sqh[k] : a[ai][bi] * rsh[k];
-    }
-  // phase 2: X = L^{-1}
-  double b[4][4];
+      for (int k = 0; k < PB; ++k) {
+        const double d = __shfl_sync(0xffffffffu, a[k], k);
+        if (!(d > 0.0) && first_bad == 0) first_bad = c0 + k + 1;
+        const double invd = 1.0 / d;
+        const double u = a[k];
+        const double w = u * invd;
 #pragma unroll
-  for (int ai = 0; ai < 4; ++ai)
-#pragma unroll
-    for (int bi = 0; bi < 4; ++bi) b[ai][bi] = (ty + 32 * ai == tx + 32 * bi) ? 1.0 : 0.0;
-#pragma unroll
-  for (int bj = 0; bj < 4; ++bj) {
-    for (int tj = 0; tj < 32; ++tj) {
-      const int j = bj * 32 + tj;
-      double* row = colbuf + (j & 1) * (CK_NB + 8);
-      if (ty == tj) {
-        const double rs = rsh[j];
-#pragma unroll
-        for (int bi = 0; bi <= bj; ++bi) {
-          const double xv = b[bj][bi] * rs;
-          b[bj][bi] = xv;
-          row[tx + 32 * bi] = xv;
+        for (int j = k + 1; j < PB; ++j) {
+          const double ujk = __shfl_sync(0xffffffffu, u, j);
+          a[j] = fma(-w, ujk, a[j]);
         }
+        const double sq = sqrt(d);
+        const double rs = 1.0 / sq;
+        a[k] = (lane == k) ? sq : u * rs;
+        if (lane == k) rsd[c0 + k] = rs;
       }
-      __syncthreads();
+      if (lane == 0 && first_bad != 0 && bad == 0) bad = first_bad;
 #pragma unroll
-      for (int ai = bj; ai < 4; ++ai) {
-        const int i = ty + 32 * ai;
-        if (i > j) {
-          const double lij = Lsh[j * CK_NB + i];
+      for (int k = 0; k < PB; ++k)
+        if (k <= lane) As[(c0 + lane) * P_LDA + c0 + k] = a[k];
+      __syncwarp();
+      // ---- X_d = L_d^{-1}, lane = column c: forward substitution on e_c; L read by broadcast
+      double x[PB];
 #pragma unroll
-          for (int bi = 0; bi <= bj; ++bi) b[ai][bi] -= lij * row[tx + 32 * bi];
-        }
+      for (int i = 0; i < PB; ++i) x[i] = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < PB; ++k) {
+        x[k] *= rsd[c0 + k];
+#pragma unroll
+        for (int i = k + 1; i < PB; ++i) x[i] = fma(-As[(c0 + i) * P_LDA + c0 + k], x[k], x[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < PB; ++i) Xdj[i * P_LDX + lane] = x[i];
+    }
+    __syncthreads();
+    const int r_begin = c0 + PB;            // first row below the panel
+    const int nt = (CK_NB - r_begin) / 8;   // 8-row tiles below
+    // ---- panel: P = A[below, c0:c0+32] X_d^T, one 8-row tile (4 output tiles) per warp pass, in place
+    for (int rt = warp; rt < nt; rt += NW) {
+      const int r0 = r_begin + 8 * rt;
+      double af[8];
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) af[ks] = As[(r0 + g4) * P_LDA + c0 + 4 * ks + t4];
+      double acc[4][2];
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        acc[n][0] = 0.0;
+        acc[n][1] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) dmma884(acc[n][0], acc[n][1], af[ks], Xdj[(8 * n + g4) * P_LDX + 4 * ks + t4]);
+      }
+      __syncwarp();  // every lane has its operand fragments before the tile row is overwritten
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        As[(r0 + g4) * P_LDA + c0 + 8 * n + 2 * t4] = acc[n][0];
+        As[(r0 + g4) * P_LDA + c0 + 8 * n + 2 * t4 + 1] = acc[n][1];
       }
     }
+    __syncthreads();
+    // ---- trailing: A[below, below] -= P P^T on the lower 8x8 tiles
+    const int ntile = nt * (nt + 1) / 2;
+    for (int t = warp; t < ntile; t += NW) {
+      int ti = 0;
+      while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+      const int tj = t - ti * (ti + 1) / 2;
+      const int ri = r_begin + 8 * ti, rj = r_begin + 8 * tj;
+      double* c = As + (ri + g4) * P_LDA + rj + 2 * t4;
+      double acc0 = -c[0], acc1 = -c[1];
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks)
+        dmma884(acc0, acc1, As[(ri + g4) * P_LDA + c0 + 4 * ks + t4], As[(rj + g4) * P_LDA + c0 + 4 * ks + t4]);
+      const bool diag = (ti == tj);  // keep the strict upper triangle of the block untouched (scratch / zeros)
+      if (!diag || 2 * t4 <= g4) c[0] = -acc0;
+      if (!diag || 2 * t4 + 1 <= g4) c[1] = -acc1;
+    }
+    __syncthreads();
   }
+
+  // ---- off-diagonal blocks of X = L^{-1}: X_ij = -X_d,i * S_ij, S_ij = sum_{k=j}^{i-1} L_ik X_kj (X_jj = X_d,j).
+  // X_ij (i > j) lives in the unused upper block (j, i) of As: element [r][c] at As[(32 j + r) * P_LDA + 32 i + c].
+  constexpr int NBK = CK_NB / PB;
+  for (int dist = 1; dist < NBK; ++dist) {
+    const int npair = NBK - dist;
+    // stage 1: S_ij -> scratch block (j, i)
+    for (int t = warp; t < npair * 16; t += NW) {
+      const int j = t / 16, i = j + dist, mt = (t % 16) / 4, nt_ = t % 4;
+      double acc0 = 0.0, acc1 = 0.0;
+      for (int k = j; k < i; ++k) {
+        const double* Lik = As + (PB * i + 8 * mt + g4) * P_LDA + PB * k + t4;        // A(m, kk) = L_ik[m][kk]
+        const double* Xkj = (k == j) ? (Xd + j * PB * P_LDX + t4 * P_LDX + 8 * nt_ + g4)  // B(kk, n) = X_kj[kk][n]
+                                     : (As + (PB * j + t4) * P_LDA + PB * k + 8 * nt_ + g4);
+        const int ldb = (k == j) ? P_LDX : P_LDA;
 #pragma unroll
-  for (int ai = 0; ai < 4; ++ai)
-#pragma unroll
-    for (int bi = 0; bi < 4; ++bi) {
-      const int i = ty + 32 * ai, c = tx + 32 * bi;
-      X[i * CK_NB + c] = (c <= i) ? b[ai][bi] : 0.0;
+        for (int ks = 0; ks < 8; ++ks) dmma884(acc0, acc1, Lik[4 * ks], Xkj[4 * ks * ldb]);
+      }
+      double* s = As + (PB * j + 8 * mt + g4) * P_LDA + PB * i + 8 * nt_ + 2 * t4;
+      s[0] = acc0;
+      s[1] = acc1;
     }
+    __syncthreads();
+    // stage 2: X_ij = -X_d,i * S_ij (in place: all tiles are computed into registers before any is written)
+    double out[3][2];  // at most 48 tiles over 16 warps
+    int slot = 0;
+    for (int t = warp; t < npair * 16; t += NW, ++slot) {
+      const int j = t / 16, i = j + dist, mt = (t % 16) / 4, nt_ = t % 4;
+      double acc0 = 0.0, acc1 = 0.0;
+      const double* Xi = Xd + i * PB * P_LDX + (8 * mt + g4) * P_LDX + t4;            // A(m, kk) = X_d,i[m][kk]
+      const double* S = As + (PB * j + t4) * P_LDA + PB * i + 8 * nt_ + g4;           // B(kk, n) = S[kk][n]
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) dmma884(acc0, acc1, Xi[4 * ks], S[4 * ks * P_LDA]);
+      out[slot][0] = -acc0;
+      out[slot][1] = -acc1;
+    }
+    __syncthreads();
+    slot = 0;
+    for (int t = warp; t < npair * 16; t += NW, ++slot) {
+      const int j = t / 16, i = j + dist, mt = (t % 16) / 4, nt_ = t % 4;
+      double* s = As + (PB * j + 8 * mt + g4) * P_LDA + PB * i + 8 * nt_ + 2 * t4;
+      s[0] = out[slot][0];
+      s[1] = out[slot][1];
+    }
+    __syncthreads();
+  }
+
+  // ---- results: L in place (lower triangle of the valid part), X dense with an explicit zero upper triangle
+  for (int idx = tid; idx < CK_NB * CK_NB; idx += P_THREADS) {
+    const int i = idx / CK_NB, k = idx % CK_NB;
+    if (i < nb && k <= i) A[(long long)i * ld + k] = As[i * P_LDA + k];
+    const int bi = i / PB, bj = k / PB, r = i % PB, c = k % PB;
+    double xv = 0.0;
+    if (bi == bj) xv = Xd[bi * PB * P_LDX + r * P_LDX + c];
+    else if (bi > bj) xv = As[(PB * bj + r) * P_LDA + PB * bi + c];
+    X[i * CK_NB + k] = xv;
+  }
   if (tid == 0 && bad != 0 && *info == 0) *info = k0 + bad;
 }
 
@@ -490,7 +554,7 @@ static int potf2_launch(double* a, long long ld, int nb, double* x, int* info, i
     CK_CUDA(cudaFuncSetAttribute(ck_potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     attr_done = true;
   }
-  ck_potf2_inv_kernel<<<1, 1024, SMEM, st>>>(a, ld, nb, x, info, k0);
+  ck_potf2_inv_kernel<<<1, P_THREADS, SMEM, st>>>(a, ld, nb, x, info, k0);
   CK_LAUNCH_CHECK();
   return CK_OK;
 }
@@ -570,22 +634,36 @@ static int lookahead_enabled() {
   }
   return v;
 }
-static int side_stream(SideStream** out) {
-  static SideStream table[64];
+// One side stream per (device, caller stream), so that independent factorisations enqueued on different
+// caller streams (batched windows) do not serialise their panel chains on a shared side stream.
+static int side_stream(cudaStream_t caller, SideStream** out) {
+  constexpr int CAP = 64;
+  struct Slot { int dev; cudaStream_t caller; SideStream* s; };
+  static Slot slots[CAP];
+  static int used = 0;
   static std::mutex mu;
   int dev = 0;
   CK_CUDA(cudaGetDevice(&dev));
-  CK_REQUIRE(dev >= 0 && dev < 64, "device index %d out of range", dev);
   std::lock_guard<std::mutex> lock(mu);
-  SideStream& t = table[dev];
-  if (!t.s) {
-    int lo = 0, hi = 0;
-    CK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    CK_CUDA(cudaStreamCreateWithPriority(&t.s, cudaStreamNonBlocking, hi));
-    CK_CUDA(cudaEventCreateWithFlags(&t.ev_a, cudaEventDisableTiming));
-    CK_CUDA(cudaEventCreateWithFlags(&t.ev_c, cudaEventDisableTiming));
+  int fallback = -1;
+  for (int i = 0; i < used; ++i) {
+    if (slots[i].dev != dev) continue;
+    if (slots[i].caller == caller) { *out = slots[i].s; return CK_OK; }
+    if (fallback < 0) fallback = i;
   }
-  *out = &t;
+  if (used == CAP) {  // table full: share the first side stream of this device (correct, merely less concurrent)
+    CK_REQUIRE(fallback >= 0, "side-stream table full");
+    *out = slots[fallback].s;
+    return CK_OK;
+  }
+  SideStream* t = new SideStream();
+  int lo = 0, hi = 0;
+  CK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  CK_CUDA(cudaStreamCreateWithPriority(&t->s, cudaStreamNonBlocking, hi));
+  CK_CUDA(cudaEventCreateWithFlags(&t->ev_a, cudaEventDisableTiming));
+  CK_CUDA(cudaEventCreateWithFlags(&t->ev_c, cudaEventDisableTiming));
+  slots[used++] = Slot{dev, caller, t};
+  *out = t;
   return CK_OK;
 }
 
@@ -603,7 +681,7 @@ extern "C" int ck_potrf(double* a, ck_i64 n, ck_i64 ld, void* ws, int* info, voi
   int rc;
   SideStream* side = nullptr;
   if (lookahead_enabled() && nblk > 2 * agg) {
-    if ((rc = side_stream(&side))) return rc;
+    if ((rc = side_stream(st, &side))) return rc;
   }
   std::unique_lock<std::mutex> turn;
   if (side) turn = std::unique_lock<std::mutex>(side->enqueue);
@@ -690,7 +768,7 @@ extern "C" int ck_trsm_lower(const double* l, ck_i64 n, ck_i64 ld, const void* w
   int rc;
   SideStream* side = nullptr;
   if (lookahead_enabled() && nblk > 2 * agg && nrhs >= 1024) {
-    if ((rc = side_stream(&side))) return rc;
+    if ((rc = side_stream(st, &side))) return rc;
   }
   std::unique_lock<std::mutex> turn;
   if (side) turn = std::unique_lock<std::mutex>(side->enqueue);
