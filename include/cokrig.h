@@ -258,6 +258,31 @@ int ck_mg_update(const double* a_dev, ck_i64 lda, const double* b_dev, ck_i64 ld
 int ck_row_dots(const double* v_dev, ck_i64 ldv, ck_i64 nrows, ck_i64 ncols, const double* y_dev, ck_i64 ldy,
                 double* out_vy_dev, double* out_vv_dev, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * K3 (INT8 tensor-core path)  FP64-equivalent rank-k updates  C -= A B^T  by fixed-slice error-free
+ * splitting (7 balanced base-256 digits per operand, 28 int8 x int8 -> int32 slice products in TMEM,
+ * FP64 recombination in the epilogue).  ck_potrf / ck_trsm_lower use these internally for their big
+ * trailing updates (same calls the reference makes: scipy cho_factor / cho_solve,
+ * src/joint_prediction.py:68-73); they are exported for tests and tools.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Bytes of one slice buffer for a (rows x k) panel: fmt 0 = "A" operand format (128-row blocks: the
+ * rows of C), fmt 1 = "B" operand format (64-row blocks: the columns of C). */
+size_t ck_oz_slices_bytes(ck_i64 rows, ck_i64 k, int fmt);
+/* Length (doubles) of the per-row scale vector for `rows` rows (rows rounded up to 128). */
+ck_i64 ck_oz_scales_len(ck_i64 rows);
+
+/* Split the FP64 panel src (rows x k, row-major, leading dimension ld; k a multiple of 32, <= 1024) into
+ * int8 digit slices.  fmt_a_dev / fmt_b_dev (either may be NULL) receive the two operand formats,
+ * scales_dev the per-row power-of-two scales. */
+int ck_oz_split(const double* src_dev, ck_i64 ld, ck_i64 rows, ck_i64 k, void* fmt_a_dev, void* fmt_b_dev,
+                double* scales_dev, void* stream);
+
+/* C (m x n, FP64, row-major) -= A B^T from split operands: A-format slices + scales of the m-row panel,
+ * B-format slices + scales of the n-row panel.  lower != 0: only entries with column <= row are updated. */
+int ck_oz_gemm(const void* a_slices_dev, const double* a_scales_dev, ck_i64 m, const void* b_slices_dev,
+               const double* b_scales_dev, ck_i64 n, ck_i64 k, double* c_dev, ck_i64 ldc, int lower, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

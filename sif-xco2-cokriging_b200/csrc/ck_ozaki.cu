@@ -1,0 +1,470 @@
+// ck_ozaki.cu -- FP64-equivalent rank-K updates  C -= A B^T  on the INT8 tensor cores of sm_100a
+// (tcgen05.mma kind::i8, accumulators in TMEM), used for the O(N^3) trailing updates of the blocked
+// Cholesky and of the multi-right-hand-side triangular solve (ck_chol.cu).
+//
+// Scheme (Ozaki-style error-free splitting with a fixed number of slices):
+//   every row of an operand panel (K <= 1024 columns) is scaled by a power of two so that |a| <= 0.98 and
+//   rounded ONCE to a 55-bit fixed-point integer Q (the only rounding of the operands, 2^-56 relative to the
+//   row maximum -- below FP64's own 2^-53), then recoded EXACTLY into S = 7 balanced base-256 digits
+//   d_0..d_6 in [-128, 127]:   a = 2^(e-7) sum_p d_p 2^(-8p).
+//   The product panel is   A B^T = s_a s_b sum_g 2^(-8g) G_g ,  G_g = sum_{p+q=g} A_p B_q^T   (int8 x int8 -> int32,
+//   exact: |G_g| <= 7 * 1024 * 2^14 < 2^31).  Groups g = 0..6 are kept (28 slice products); the dropped groups
+//   g >= 7 are zero-mean terms below 2^-56 of (row max) x (column max) per k -- the same order as the FP64
+//   rounding of a DMMA update.  tools/ozaki_sim.py reproduces the scheme in numpy (Cholesky + solve errors
+//   equal to LAPACK's to the last digit on the C1 system).
+//
+// Kernel (ck_oz_gemm_kernel, persistent, one CTA per SM, 192 threads, warp-specialised):
+//   CTA tile 128 (rows of A) x 64 (rows of B); ALL seven group accumulators live in TMEM at once
+//   (7 x 64 = 448 of 512 columns), so every operand byte is fetched once per tile and the FP64 epilogue runs
+//   once per tile (K = 1024 deep), not once per group.
+//   warp 0  producer : per 32-deep k chunk one cp.async.bulk of the 7 A slices (28 KB) and one of the 7 B slices
+//                      (14 KB) into a 4-stage shared-memory ring (mbarrier complete_tx).  The split kernel writes
+//                      the slices to global memory already in the UMMA canonical K-major (no-swizzle) core-matrix
+//                      order, so a stage is two contiguous copies -- no tensor maps.
+//   warp 1  MMA      : one thread issues 10 tcgen05.mma per chunk instead of 28: the B slices q..q+3 are adjacent
+//                      in shared memory with the row-group stride of one slice, so A_p x [B_q..B_q+3] is ONE
+//                      M=128, N=256 instruction whose 256 accumulator columns are exactly the group blocks
+//                      p+q..p+q+3 (A is read 10 times per chunk instead of 28).
+//   warps 2-5 epilogue: tcgen05.ld the 7 int32 group blocks, Horner in FP64 (v = v 2^-8 + G_g, exact
+//                      conversions), scale by s_a s_b (powers of two: exact) and C -= v.
+#include <stdint.h>
+#include <stdlib.h>
+#include "ck_common.cuh"
+
+namespace {
+
+constexpr int OZ_S = 7;                        // slices per operand
+constexpr int OZ_QBITS = 7 + 8 * (OZ_S - 1);   // 55-bit fixed point
+constexpr int OZ_KC = 32;                      // int8 k per chunk == K of one tcgen05.mma kind::i8
+constexpr int OZ_TM = 128, OZ_TN = 64;
+constexpr int OZ_A_SLICE = OZ_TM * OZ_KC;      // 4096 B: [ku 2][row group 16][row 8][16 B]
+constexpr int OZ_A_STAGE = OZ_S * OZ_A_SLICE;  // 28672 B: [p 7][slice]
+constexpr int OZ_B_KU = OZ_S * OZ_TN * 16;     // 7168 B:  [q 7][row group 8][row 8][16 B]
+constexpr int OZ_B_STAGE = 2 * OZ_B_KU;        // 14336 B: [ku 2][...]
+constexpr int OZ_STAGE = OZ_A_STAGE + OZ_B_STAGE;
+constexpr int OZ_NSTAGE = 4;
+constexpr int OZ_THREADS = 192;
+constexpr int OZ_TMEM_COLS = 512;
+constexpr size_t OZ_SMEM = (size_t)OZ_NSTAGE * OZ_STAGE + 1024 /* alignment slack */ + 256 /* barriers */;
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol error must end in a trap (an error the host sees), never in a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, int (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major, no swizzle ("interleave"): core matrix = 8 rows x 16 B contiguous (128 B);
+// LBO = byte distance between the two 16-byte k units of one K=32 instruction, SBO = byte distance between
+// consecutive 8-row groups along M / N (cute::UMMA::SmemDescriptor; layout ((8,n),2):((1,SBO),LBO) in 16-byte units).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+// instruction descriptor: D = S32 (bits 4-5 = 2), A, B = signed int8 (bits 7-9, 10-12 = 1), both K-major, N >> 3 at 17, M >> 4 at 24
+__device__ __forceinline__ uint32_t umma_idesc_i8(int n) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(OZ_TM >> 4) << 24);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// Split: FP64 panel rows -> 7 int8 digit slices in the two operand formats + per-row scale 2^(e-7)
+//   A format (128-row blocks):  [rb][kc][p][ku][row group 16][row 8][16 B]
+//   B format ( 64-row blocks):  [hb][kc][ku][q][row group 8][row 8][16 B]
+// One CTA = 8 rows (one row group), one warp per row, a lane owns the 16-element k units lane and lane + 32.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ck_oz_split_kernel(const double* __restrict__ src, long long ld, long long rows, int K,
+                                                          uint8_t* __restrict__ fa, uint8_t* __restrict__ fb,
+                                                          long long rows_b_pad, double* __restrict__ scales, int vec) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const long long row = (long long)blockIdx.x * 8 + w;
+  const int units = K >> 4, kcn = K >> 5;
+  const bool live = row < rows;
+  double x[2][16];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int u = lane + 32 * h;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[h][i] = 0.0;
+    if (live && u < units) {
+      const double* p = src + row * ld + 16 * u;
+      if (vec) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const double2 v = *reinterpret_cast<const double2*>(p + 2 * i);
+          x[h][2 * i] = v.x;
+          x[h][2 * i + 1] = v.y;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[h][i] = p[i];
+      }
+    }
+  }
+  double amax = 0.0;
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) amax = fmax(amax, fabs(x[h][i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  int ex = 0;
+  if (amax > 0.0 && amax < 1.0e300) {
+    const double f = frexp(amax, &ex);  // amax = f 2^ex, f in [0.5, 1)
+    if (f > 0.98) ++ex;                 // |a| 2^-ex <= 0.98: the leading digit stays inside [-126, 126]
+    if (ex < -900) ex = -900;
+  }
+  const double up = __hiloint2double((1023 + OZ_QBITS - ex) << 20, 0);  // 2^(55 - ex), exact scaling
+  if (lane == 0) scales[row] = (live && amax > 0.0) ? __hiloint2double((1023 + ex - 7) << 20, 0) : 0.0;
+
+  const long long rb = row >> 7, hb = row >> 6;
+  const int rg16 = (int)(row & 127) >> 3, rg8 = (int)(row & 63) >> 3, r8 = (int)(row & 7);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int u = lane + 32 * h;
+    if (u >= units) continue;
+    uint32_t wd[OZ_S][4];
+#pragma unroll
+    for (int p = 0; p < OZ_S; ++p)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) wd[p][j] = 0u;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      long long q = __double2ll_rn(x[h][i] * up);
+#pragma unroll
+      for (int p = OZ_S - 1; p >= 0; --p) {
+        const int d = (int)((q + 128) & 255) - 128;  // balanced digit in [-128, 127]
+        q = (q - d) >> 8;
+        wd[p][i >> 2] |= (uint32_t)(d & 255) << (8 * (i & 3));
+      }
+    }
+    const int kc = u >> 1, ku = u & 1;
+    if (fa) {
+      uint8_t* base = fa + ((size_t)(rb * kcn + kc)) * OZ_A_STAGE + ku * 2048 + rg16 * 128 + r8 * 16;
+#pragma unroll
+      for (int p = 0; p < OZ_S; ++p)
+        *reinterpret_cast<uint4*>(base + p * OZ_A_SLICE) = make_uint4(wd[p][0], wd[p][1], wd[p][2], wd[p][3]);
+    }
+    if (fb && row < rows_b_pad) {
+      uint8_t* base = fb + ((size_t)(hb * kcn + kc)) * OZ_B_STAGE + ku * OZ_B_KU + rg8 * 128 + r8 * 16;
+#pragma unroll
+      for (int p = 0; p < OZ_S; ++p)
+        *reinterpret_cast<uint4*>(base + p * (OZ_TN * 16)) = make_uint4(wd[p][0], wd[p][1], wd[p][2], wd[p][3]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GEMM
+// ------------------------------------------------------------------------------------------------
+struct OzGemmArgs {
+  const uint8_t* a;   // A-format slices of the M-side panel
+  const uint8_t* b;   // B-format slices of the N-side panel
+  const double* sa;   // row scales of A (length >= 128 ni)
+  const double* sb;   // row scales of B (length >= 64 nj)
+  double* c;
+  long long ldc, m, n;
+  int kcn;            // K / 32
+  int ni, nj;         // 128-row blocks of A, 64-row blocks of B
+  int lower;          // 1: only entries with col <= row are updated (tiles above the diagonal are skipped)
+  int tri;            // 1: triangular virtual tile space (square lower update), 0: rectangular
+  long long nvirt;    // virtual tiles
+  int desc_swap;      // debug: exchange LBO / SBO
+  int vec;            // C is 16-byte aligned with an even leading dimension
+};
+
+// virtual tile t -> (I, j).  Tiles are ordered in super-rows of 8 row blocks, inside a super-row column-major
+// (j outer, I inner), so that the ~148 tiles in flight share 8 A blocks and ~18 B blocks (L2 reuse).
+__device__ __forceinline__ bool oz_decode(const OzGemmArgs& g, long long t, int& I, int& j) {
+  long long s, u;
+  if (g.tri) {
+    s = (long long)((sqrt(1.0 + (double)t * (1.0 / 16.0)) - 1.0) * 0.5);
+    while (64 * (s + 1) * (s + 2) <= t) ++s;
+    while (64 * s * (s + 1) > t) --s;
+    u = t - 64 * s * (s + 1);
+  } else {
+    const long long w = 8LL * g.nj;
+    s = t / w;
+    u = t - s * w;
+  }
+  j = (int)(u >> 3);
+  I = (int)(8 * s + (u & 7));
+  return I < g.ni && j < g.nj && (!g.lower || j <= 2 * I + 1);
+}
+
+__global__ void __launch_bounds__(OZ_THREADS, 1) ck_oz_gemm_kernel(OzGemmArgs g) {
+  extern __shared__ uint8_t oz_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)oz_smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)OZ_NSTAGE * OZ_STAGE);
+  // bars[0..3] full, [4..7] empty, [8] tmem_full, [9] tmem_empty, then the TMEM base address
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (OZ_NSTAGE + s); };
+  const uint32_t tfull_bar = bar0 + 8u * (2 * OZ_NSTAGE), tempty_bar = bar0 + 8u * (2 * OZ_NSTAGE + 1);
+  const uint32_t smem0 = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < OZ_NSTAGE; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tfull_bar, 1);
+    mbar_init(tempty_bar, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)OZ_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long t = blockIdx.x; t < g.nvirt; t += gridDim.x) {
+        int I, j;
+        if (!oz_decode(g, t, I, j)) continue;
+        const uint8_t* ga = g.a + (size_t)I * g.kcn * OZ_A_STAGE;
+        const uint8_t* gb = g.b + (size_t)j * g.kcn * OZ_B_STAGE;
+        for (int kc = 0; kc < g.kcn; ++kc) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), OZ_STAGE);
+          const uint32_t dst = smem0 + (uint32_t)stage * OZ_STAGE;
+          bulk_g2s(dst, ga + (size_t)kc * OZ_A_STAGE, OZ_A_STAGE, full_bar(stage));
+          bulk_g2s(dst + OZ_A_STAGE, gb + (size_t)kc * OZ_B_STAGE, OZ_B_STAGE, full_bar(stage));
+          if (++stage == OZ_NSTAGE) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, aphase = 0;
+      const uint32_t a_lbo = g.desc_swap ? 128u : 2048u, a_sbo = g.desc_swap ? 2048u : 128u;
+      const uint32_t b_lbo = g.desc_swap ? 128u : (uint32_t)OZ_B_KU, b_sbo = g.desc_swap ? (uint32_t)OZ_B_KU : 128u;
+      const uint32_t id256 = umma_idesc_i8(256), id192 = umma_idesc_i8(192), id128 = umma_idesc_i8(128), id64 = umma_idesc_i8(64);
+      for (long long t = blockIdx.x; t < g.nvirt; t += gridDim.x) {
+        int I, j;
+        if (!oz_decode(g, t, I, j)) continue;
+        mbar_wait(tempty_bar, aphase ^ 1u);
+        tc_fence_after();
+        for (int kc = 0; kc < g.kcn; ++kc) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa0 = smem0 + (uint32_t)stage * OZ_STAGE, sb0 = sa0 + OZ_A_STAGE;
+          const uint32_t acc0 = kc > 0 ? 1u : 0u;
+          auto A = [&](int p) { return umma_desc(sa0 + p * OZ_A_SLICE, a_lbo, a_sbo); };
+          auto B = [&](int q) { return umma_desc(sb0 + q * (OZ_TN * 16), b_lbo, b_sbo); };
+          auto D = [&](int gblk) { return tmem + (uint32_t)(gblk * OZ_TN); };
+          // A_p x [B_q0 .. B_q0+nq-1] -> group blocks p+q0 .. (one instruction, N = 64 nq)
+          tc_mma_i8(D(0), A(0), B(0), id256, acc0);  // p = 0 touches every block first: it alone (re)initialises
+          tc_mma_i8(D(4), A(0), B(4), id192, acc0);
+          tc_mma_i8(D(1), A(1), B(0), id256, 1u);
+          tc_mma_i8(D(5), A(1), B(4), id128, 1u);
+          tc_mma_i8(D(2), A(2), B(0), id256, 1u);
+          tc_mma_i8(D(6), A(2), B(4), id64, 1u);
+          tc_mma_i8(D(3), A(3), B(0), id256, 1u);
+          tc_mma_i8(D(4), A(4), B(0), id192, 1u);
+          tc_mma_i8(D(5), A(5), B(0), id128, 1u);
+          tc_mma_i8(D(6), A(6), B(0), id64, 1u);
+          tc_commit(empty_bar(stage));  // frees the stage when these MMAs have read it
+          if (++stage == OZ_NSTAGE) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit(tfull_bar);
+        aphase ^= 1u;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue: warps 2..5 own TMEM lane quadrants (warp % 4) =====
+    const int qd = warp & 3;
+    uint32_t aphase = 0;
+    for (long long t = blockIdx.x; t < g.nvirt; t += gridDim.x) {
+      int I, j;
+      if (!oz_decode(g, t, I, j)) continue;
+      mbar_wait(tfull_bar, aphase);
+      tc_fence_after();
+      const long long row = (long long)I * OZ_TM + 32 * qd + lane;
+      const bool row_ok = row < g.m;
+      const double srow = row_ok ? g.sa[row] : 0.0;
+      double* crow = g.c + (row_ok ? row : 0) * g.ldc;
+#pragma unroll 1
+      for (int c16 = 0; c16 < 4; ++c16) {
+        int acc[OZ_S][16];
+        const uint32_t taddr = tmem + ((uint32_t)(32 * qd) << 16) + (uint32_t)(16 * c16);
+#pragma unroll
+        for (int gb = 0; gb < OZ_S; ++gb) tc_ld16(taddr + (uint32_t)(gb * OZ_TN), acc[gb]);
+        tc_wait_ld();
+        const long long col0 = (long long)j * OZ_TN + 16 * c16;
+        double v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          double h = (double)acc[OZ_S - 1][i];
+#pragma unroll
+          for (int gb = OZ_S - 2; gb >= 0; --gb) h = fma(h, 0.00390625, (double)acc[gb][i]);
+          v[i] = h;
+        }
+        if (row_ok && col0 < g.n && (!g.lower || col0 <= row)) {
+          const bool full = g.vec && (col0 + 15 < g.n) && (!g.lower || col0 + 15 <= row);
+          if (full) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+              double2 cv = *reinterpret_cast<double2*>(crow + col0 + i);
+              cv.x -= v[i] * (srow * __ldg(g.sb + col0 + i));
+              cv.y -= v[i + 1] * (srow * __ldg(g.sb + col0 + i + 1));
+              *reinterpret_cast<double2*>(crow + col0 + i) = cv;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const long long col = col0 + i;
+              if (col < g.n && (!g.lower || col <= row)) crow[col] -= v[i] * (srow * __ldg(g.sb + col));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar);
+      aphase ^= 1u;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)OZ_TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+extern "C" size_t ck_oz_slices_bytes(ck_i64 rows, ck_i64 k, int fmt) {
+  if (rows <= 0 || k <= 0) return 0;
+  const size_t kcn = (size_t)((k + OZ_KC - 1) / OZ_KC);
+  if (fmt == 0) return (size_t)((rows + OZ_TM - 1) / OZ_TM) * kcn * OZ_A_STAGE;
+  return (size_t)((rows + OZ_TN - 1) / OZ_TN) * kcn * OZ_B_STAGE;
+}
+
+extern "C" ck_i64 ck_oz_scales_len(ck_i64 rows) { return rows <= 0 ? 0 : ((rows + OZ_TM - 1) / OZ_TM) * OZ_TM; }
+
+extern "C" int ck_oz_split(const double* src, ck_i64 ld, ck_i64 rows, ck_i64 k, void* fmt_a, void* fmt_b, double* scales,
+                           void* stream) {
+  CK_REQUIRE(rows >= 0 && k >= 0, "negative size");
+  if (rows == 0 || k == 0) return CK_OK;
+  CK_REQUIRE(src && scales && (fmt_a || fmt_b), "null pointer");
+  CK_REQUIRE(k % OZ_KC == 0 && k <= 1024, "k (%lld) must be a multiple of 32 and <= 1024", (long long)k);
+  CK_REQUIRE(ld >= k, "ld (%lld) < k (%lld)", (long long)ld, (long long)k);
+  const ck_i64 rows_pad = ck_oz_scales_len(rows);
+  const ck_i64 rows_b_pad = ((rows + OZ_TN - 1) / OZ_TN) * OZ_TN;
+  const int vec = ((((uintptr_t)src) & 15) == 0 && (ld & 1) == 0) ? 1 : 0;
+  ck_oz_split_kernel<<<(unsigned)(rows_pad / 8), 256, 0, ck_stream(stream)>>>(src, ld, rows, (int)k, static_cast<uint8_t*>(fmt_a),
+                                                                            static_cast<uint8_t*>(fmt_b), rows_b_pad, scales, vec);
+  CK_LAUNCH_CHECK();
+  return CK_OK;
+}
+
+static int oz_num_sms() {
+  static int v = 0;
+  if (v == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+  }
+  return v;
+}
+
+extern "C" int ck_oz_gemm(const void* a_slices, const double* sa, ck_i64 m, const void* b_slices, const double* sb, ck_i64 n,
+                          ck_i64 k, double* c, ck_i64 ldc, int lower, void* stream) {
+  CK_REQUIRE(m >= 0 && n >= 0 && k >= 0, "negative size");
+  if (m == 0 || n == 0 || k == 0) return CK_OK;
+  CK_REQUIRE(a_slices && b_slices && sa && sb && c, "null pointer");
+  CK_REQUIRE(k % OZ_KC == 0 && k <= 1024, "k (%lld) must be a multiple of 32 and <= 1024", (long long)k);
+  CK_REQUIRE(ldc >= n, "ldc (%lld) < n (%lld)", (long long)ldc, (long long)n);
+  CK_REQUIRE((((uintptr_t)a_slices | (uintptr_t)b_slices) & 15) == 0, "slice buffers must be 16-byte aligned");
+  static bool attr_done = false;
+  if (!attr_done) {
+    CK_CUDA(cudaFuncSetAttribute(ck_oz_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM));
+    attr_done = true;
+  }
+  OzGemmArgs g;
+  g.a = static_cast<const uint8_t*>(a_slices);
+  g.b = static_cast<const uint8_t*>(b_slices);
+  g.sa = sa; g.sb = sb; g.c = c; g.ldc = ldc; g.m = m; g.n = n;
+  g.kcn = (int)(k / OZ_KC);
+  g.ni = (int)((m + OZ_TM - 1) / OZ_TM);
+  g.nj = (int)((n + OZ_TN - 1) / OZ_TN);
+  g.lower = lower ? 1 : 0;
+  const long long srows = (g.ni + 7) / 8;
+  // the triangular tile space needs every super-row s to hold its 16 s + 16 column blocks; use it for (near-)square
+  // lower updates, the rectangular space otherwise
+  g.tri = (g.lower && (long long)g.nj >= 2LL * g.ni - 1) ? 1 : 0;
+  g.nvirt = g.tri ? 64 * srows * (srows + 1) : srows * 8LL * g.nj;
+  const char* e = getenv("CK_OZ_DESC_SWAP");
+  g.desc_swap = e ? atoi(e) : 0;
+  g.vec = ((((uintptr_t)c) & 15) == 0 && (ldc & 1) == 0) ? 1 : 0;
+  long long grid = oz_num_sms();
+  if (grid > g.nvirt) grid = g.nvirt;
+  ck_oz_gemm_kernel<<<(unsigned)grid, OZ_THREADS, OZ_SMEM, ck_stream(stream)>>>(g);
+  CK_LAUNCH_CHECK();
+  return CK_OK;
+}
