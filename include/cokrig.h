@@ -96,8 +96,10 @@ int ck_cross_cov(const double* xy0_dev, ck_i64 n0, const double* xy1_dev, ck_i64
  * K3  dense FP64 Cholesky, triangular solve, simple-cokriging prediction
  * ---------------------------------------------------------------------------------------------- */
 
-/* Scratch needed by ck_potrf for an n x n matrix (inverses of the 128 x 128 diagonal blocks of L,
- * kept for the blocked triangular solves). */
+/* Scratch needed by ck_potrf for an n x n matrix: the inverses of the 128 x 128 diagonal blocks of L (kept for
+ * the blocked triangular solves) and, for n >= 2048, the int8 digit slices of one n x 1024 panel (INT8 tensor-core
+ * updates, below).  ck_trsm_lower / ck_potrs_predict reuse the slice scratch: solves sharing one factor must not
+ * run concurrently. */
 size_t ck_potrf_workspace_bytes(ck_i64 n);
 
 /* In-place lower Cholesky A = L L^T (row-major; the strict upper triangle is not referenced and is
@@ -265,6 +267,17 @@ int ck_row_dots(const double* v_dev, ck_i64 ldv, ck_i64 nrows, ck_i64 ncols, con
  * trailing updates (same calls the reference makes: scipy cho_factor / cho_solve,
  * src/joint_prediction.py:68-73); they are exported for tests and tools.
  * ---------------------------------------------------------------------------------------------- */
+
+/* Process-wide switches of the INT8 path (negative value = leave unchanged): enabled (default 1, env CK_OZAKI)
+ * and the smallest trailing dimension handed to it (default 4096, env CK_OZ_MIN_ROWS; matrices smaller than
+ * twice that, or than 2048, are factored by the FP64 DMMA kernel alone).  The workspace size does not depend on
+ * these switches. */
+int ck_oz_configure(int enabled, ck_i64 min_rows);
+
+/* Profiling aid: when set to a device buffer of 8 x 148 int64 counters, every ck_oz_gemm launch stores per-CTA
+ * cycle counts there ([0] MMA-issue thread total, [1] waiting for operands, [2] waiting for TMEM, [4] epilogue
+ * waiting, [5] epilogue busy).  NULL switches it off (default). */
+int ck_oz_debug_buffer(void* dev_counters);
 
 /* Bytes of one slice buffer for a (rows x k) panel: fmt 0 = "A" operand format (128-row blocks: the
  * rows of C), fmt 1 = "B" operand format (64-row blocks: the columns of C). */

@@ -541,10 +541,64 @@ __global__ void ck_nll_combine_kernel(double* out, long long n) {
 // ------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------
+// INT8 tensor-core path for the big trailing updates (ck_ozaki.cu).  CK_OZAKI=0 selects the FP64 DMMA kernel
+// everywhere; CK_OZ_MIN_ROWS is the smallest trailing dimension handed to the INT8 kernel (below it the
+// persistent kernel cannot fill the machine and the DMMA kernel is used).
+// ------------------------------------------------------------------------------------------------
+static int g_oz_enabled = -1;
+static ck_i64 g_oz_min_rows = -1;
+static int oz_enabled() {
+  if (g_oz_enabled < 0) {
+    const char* e = getenv("CK_OZAKI");
+    g_oz_enabled = e ? (atoi(e) != 0) : 1;
+  }
+  return g_oz_enabled;
+}
+static ck_i64 oz_min_rows() {
+  if (g_oz_min_rows < 0) {
+    const char* e = getenv("CK_OZ_MIN_ROWS");
+    g_oz_min_rows = e ? atoll(e) : 4096;
+    if (g_oz_min_rows < 128) g_oz_min_rows = 128;
+  }
+  return g_oz_min_rows;
+}
+extern "C" int ck_oz_configure(int enabled, ck_i64 min_rows) {
+  if (enabled >= 0) g_oz_enabled = enabled ? 1 : 0;
+  if (min_rows >= 0) g_oz_min_rows = min_rows < 128 ? 128 : min_rows;
+  return CK_OK;
+}
+constexpr ck_i64 OZ_KMAX = 1024;  // deepest update one split covers (ck_oz_split)
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+static size_t xinv_bytes(ck_i64 n) {
+  const size_t nblk = (size_t)((n + CK_NB - 1) / CK_NB);
+  return align256(nblk * CK_NB * CK_NB * sizeof(double));
+}
+// scratch behind the diagonal-block inverses: A-format and B-format slices of one n x 1024 panel + two scale vectors
+struct OzScratch {
+  void* fa; void* fb; double* sa; double* sb;
+};
+// The workspace carries the slice scratch for every n >= OZ_WS_MIN_N whatever the switches say, so a workspace
+// sized under one configuration stays valid under any other.
+constexpr ck_i64 OZ_WS_MIN_N = 2048;
+static bool oz_wanted(ck_i64 n) { return oz_enabled() && n >= OZ_WS_MIN_N && n >= 2 * oz_min_rows(); }
+static OzScratch oz_scratch(void* ws, ck_i64 n) {
+  char* p = static_cast<char*>(ws) + xinv_bytes(n);
+  OzScratch s;
+  s.fa = p; p += align256(ck_oz_slices_bytes(n, OZ_KMAX, 0));
+  s.fb = p; p += align256(ck_oz_slices_bytes(n, OZ_KMAX, 1));
+  s.sa = reinterpret_cast<double*>(p); p += align256((size_t)ck_oz_scales_len(n) * sizeof(double));
+  s.sb = reinterpret_cast<double*>(p);
+  return s;
+}
+
 extern "C" size_t ck_potrf_workspace_bytes(ck_i64 n) {
   if (n <= 0) return 0;
-  const size_t nblk = (size_t)((n + CK_NB - 1) / CK_NB);
-  return nblk * CK_NB * CK_NB * sizeof(double);
+  size_t b = xinv_bytes(n);
+  if (n >= OZ_WS_MIN_N)
+    b += align256(ck_oz_slices_bytes(n, OZ_KMAX, 0)) + align256(ck_oz_slices_bytes(n, OZ_KMAX, 1)) +
+         2 * align256((size_t)ck_oz_scales_len(n) * sizeof(double));
+  return b;
 }
 
 static int potf2_launch(double* a, long long ld, int nb, double* x, int* info, int k0, cudaStream_t st) {
@@ -679,6 +733,30 @@ extern "C" int ck_potrf(double* a, ck_i64 n, ck_i64 ld, void* ws, int* info, voi
   const ck_i64 nblk = (n + CK_NB - 1) / CK_NB;
   const int agg = agg_blocks();
   int rc;
+  if (oz_wanted(n) && (ck_i64)agg * CK_NB <= OZ_KMAX) {
+    // Big trailing updates on the INT8 tensor cores: per aggregate, the panel chain (FP64 DMMA, recursive), one split
+    // of the finished panel into digit slices, one persistent tcgen05 kernel over the lower tiles of the trailing matrix.
+    const OzScratch z = oz_scratch(ws, n);
+    for (ck_i64 b0 = 0; b0 < nblk; b0 += agg) {
+      const ck_i64 b1 = b0 + agg < nblk ? b0 + agg : nblk;
+      if ((rc = factor_range(c, b0, b1))) return rc;
+      const ck_i64 k0 = c.s(b0), k1 = c.s(b1);
+      if (k1 >= n) break;
+      const ck_i64 rows = n - k1, kk = k1 - k0;
+      if (rows >= oz_min_rows() && kk % 32 == 0) {
+        if ((rc = ck_oz_split(a + k1 * ld + k0, ld, rows, kk, z.fa, z.fb, z.sa, stream))) return rc;
+        if ((rc = ck_oz_gemm(z.fa, z.sa, rows, z.fb, z.sa, rows, kk, a + k1 * ld + k1, ld, 1, stream))) return rc;
+      } else {
+        GemmArgs u;  // A[k1:, k1:] -= P P^T, P = A[k1:, k0:k1], lower tiles
+        u.A = a + k1 * ld + k0; u.lda = ld;
+        u.B = a + k1 * ld + k0; u.ldb = ld;
+        u.C = a + k1 * ld + k1; u.ldc = ld;
+        u.M = rows; u.N = rows; u.K = kk; u.mode = 1; u.lower_only = 1;
+        if ((rc = gemm_launch<4, 2>(u, st))) return rc;
+      }
+    }
+    return CK_OK;
+  }
   SideStream* side = nullptr;
   if (lookahead_enabled() && nblk > 2 * agg) {
     if ((rc = side_stream(st, &side))) return rc;
@@ -766,6 +844,31 @@ extern "C" int ck_trsm_lower(const double* l, ck_i64 n, ck_i64 ld, const void* w
   const ck_i64 nblk = (n + CK_NB - 1) / CK_NB;
   const int agg = agg_blocks();
   int rc;
+  if (oz_wanted(n) && (ck_i64)agg * CK_NB <= OZ_KMAX && nrhs >= 1024 && nrhs <= n) {
+    // INT8 tensor-core updates (see ck_potrf).  The slice scratch lives behind the block inverses in the
+    // factorisation workspace: solves that share one factor must not run concurrently.
+    const OzScratch z = oz_scratch(const_cast<void*>(ws), n);
+    for (ck_i64 b0 = 0; b0 < nblk; b0 += agg) {
+      const ck_i64 b1 = b0 + agg < nblk ? b0 + agg : nblk;
+      if ((rc = solve_range(c, b0, b1))) return rc;
+      const ck_i64 k0 = c.s(b0), k1 = c.s(b1);
+      if (k1 >= n) break;
+      const ck_i64 cols = n - k1, kk = k1 - k0;
+      if (cols >= oz_min_rows() && kk % 32 == 0) {
+        if ((rc = ck_oz_split(rhs + k0, ld_rhs, nrhs, kk, z.fa, nullptr, z.sa, stream))) return rc;
+        if ((rc = ck_oz_split(l + k1 * ld + k0, ld, cols, kk, nullptr, z.fb, z.sb, stream))) return rc;
+        if ((rc = ck_oz_gemm(z.fa, z.sa, nrhs, z.fb, z.sb, cols, kk, rhs + k1, ld_rhs, 0, stream))) return rc;
+      } else {
+        GemmArgs r;  // R[:, k1:] -= V[:, k0:k1] L[k1:, k0:k1]^T
+        r.A = rhs + k0; r.lda = ld_rhs;
+        r.B = l + k1 * ld + k0; r.ldb = ld;
+        r.C = rhs + k1; r.ldc = ld_rhs;
+        r.M = nrhs; r.N = cols; r.K = kk; r.mode = 1; r.lower_only = 0;
+        if ((rc = gemm_launch<4, 2>(r, st))) return rc;
+      }
+    }
+    return CK_OK;
+  }
   SideStream* side = nullptr;
   if (lookahead_enabled() && nblk > 2 * agg && nrhs >= 1024) {
     if ((rc = side_stream(st, &side))) return rc;

@@ -101,6 +101,11 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, int (&r)[16]) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, int (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor, K-major, no swizzle ("interleave"): core matrix = 8 rows x 16 B contiguous (128 B);
@@ -220,6 +225,7 @@ struct OzGemmArgs {
   long long nvirt;    // virtual tiles
   int desc_swap;      // debug: exchange LBO / SBO
   int vec;            // C is 16-byte aligned with an even leading dimension
+  long long* dbg;     // optional per-CTA cycle counters (8 per CTA), see ck_oz_debug_buffer
 };
 
 // virtual tile t -> (I, j).  Tiles are ordered in super-rows of 8 row blocks, inside a super-row column-major
@@ -300,17 +306,23 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ck_oz_gemm_kernel(OzGemmArgs g)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0, aphase = 0;
+      long long t_full = 0, t_tempty = 0;
+      const long long t_start = clock64();
       const uint32_t a_lbo = g.desc_swap ? 128u : 2048u, a_sbo = g.desc_swap ? 2048u : 128u;
       const uint32_t b_lbo = g.desc_swap ? 128u : (uint32_t)OZ_B_KU, b_sbo = g.desc_swap ? (uint32_t)OZ_B_KU : 128u;
       const uint32_t id256 = umma_idesc_i8(256), id192 = umma_idesc_i8(192), id128 = umma_idesc_i8(128), id64 = umma_idesc_i8(64);
       for (long long t = blockIdx.x; t < g.nvirt; t += gridDim.x) {
         int I, j;
         if (!oz_decode(g, t, I, j)) continue;
+        long long w0 = clock64();
         mbar_wait(tempty_bar, aphase ^ 1u);
         tc_fence_after();
+        t_tempty += clock64() - w0;
         for (int kc = 0; kc < g.kcn; ++kc) {
+          w0 = clock64();
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
+          t_full += clock64() - w0;
           const uint32_t sa0 = smem0 + (uint32_t)stage * OZ_STAGE, sb0 = sa0 + OZ_A_STAGE;
           const uint32_t acc0 = kc > 0 ? 1u : 0u;
           auto A = [&](int p) { return umma_desc(sa0 + p * OZ_A_SLICE, a_lbo, a_sbo); };
@@ -333,59 +345,84 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ck_oz_gemm_kernel(OzGemmArgs g)
         tc_commit(tfull_bar);
         aphase ^= 1u;
       }
+      if (g.dbg) {
+        g.dbg[blockIdx.x * 8 + 0] = clock64() - t_start;  // MMA-issue thread: total, waiting for operands, waiting for TMEM
+        g.dbg[blockIdx.x * 8 + 1] = t_full;
+        g.dbg[blockIdx.x * 8 + 2] = t_tempty;
+      }
     }
     __syncwarp();
   } else {
-    // ===== epilogue: warps 2..5 own TMEM lane quadrants (warp % 4) =====
+    // ===== epilogue: warps 2..5 own TMEM lane quadrants (warp % 4); a thread owns one row x 64 columns =====
+    // The C row segment is loaded BEFORE waiting for the accumulators (its latency hides behind the MMAs of the
+    // tile), TMEM is released as soon as the last block has been read, and the stores are issued after that, so
+    // only TMEM reads + the FP64 recombination sit between two tiles of the MMA stream.
     const int qd = warp & 3;
     uint32_t aphase = 0;
+    long long t_busy = 0, t_wait = 0;
     for (long long t = blockIdx.x; t < g.nvirt; t += gridDim.x) {
       int I, j;
       if (!oz_decode(g, t, I, j)) continue;
-      mbar_wait(tfull_bar, aphase);
-      tc_fence_after();
       const long long row = (long long)I * OZ_TM + 32 * qd + lane;
+      const long long cb = (long long)j * OZ_TN;
       const bool row_ok = row < g.m;
       const double srow = row_ok ? g.sa[row] : 0.0;
-      double* crow = g.c + (row_ok ? row : 0) * g.ldc;
-#pragma unroll 1
-      for (int c16 = 0; c16 < 4; ++c16) {
-        int acc[OZ_S][16];
-        const uint32_t taddr = tmem + ((uint32_t)(32 * qd) << 16) + (uint32_t)(16 * c16);
+      double* crow = g.c + (row_ok ? row : 0) * g.ldc + cb;
+      const double sb_lo = (cb + lane < g.n) ? __ldg(g.sb + cb + lane) : 0.0;
+      const double sb_hi = (cb + 32 + lane < g.n) ? __ldg(g.sb + cb + 32 + lane) : 0.0;
+      const bool fast = g.vec && row_ok && (cb + OZ_TN - 1 < g.n) && (!g.lower || cb + OZ_TN - 1 <= row);
+      double creg[OZ_TN];
+      if (fast) {
 #pragma unroll
-        for (int gb = 0; gb < OZ_S; ++gb) tc_ld16(taddr + (uint32_t)(gb * OZ_TN), acc[gb]);
+        for (int i = 0; i < OZ_TN; i += 2) {
+          const double2 cv = *reinterpret_cast<const double2*>(crow + i);
+          creg[i] = cv.x;
+          creg[i + 1] = cv.y;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < OZ_TN; ++i)
+          creg[i] = (row_ok && cb + i < g.n && (!g.lower || cb + i <= row)) ? crow[i] : 0.0;
+      }
+      const long long w0 = clock64();
+      mbar_wait(tfull_bar, aphase);
+      tc_fence_after();
+      const long long w1 = clock64();
+#pragma unroll
+      for (int c8 = 0; c8 < OZ_TN / 8; ++c8) {
+        int acc[OZ_S][8];
+        const uint32_t taddr = tmem + ((uint32_t)(32 * qd) << 16) + (uint32_t)(8 * c8);
+#pragma unroll
+        for (int gb = 0; gb < OZ_S; ++gb) tc_ld8(taddr + (uint32_t)(gb * OZ_TN), acc[gb]);
         tc_wait_ld();
-        const long long col0 = (long long)j * OZ_TN + 16 * c16;
-        double v[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < 8; ++i) {
           double h = (double)acc[OZ_S - 1][i];
 #pragma unroll
           for (int gb = OZ_S - 2; gb >= 0; --gb) h = fma(h, 0.00390625, (double)acc[gb][i]);
-          v[i] = h;
-        }
-        if (row_ok && col0 < g.n && (!g.lower || col0 <= row)) {
-          const bool full = g.vec && (col0 + 15 < g.n) && (!g.lower || col0 + 15 <= row);
-          if (full) {
-#pragma unroll
-            for (int i = 0; i < 16; i += 2) {
-              double2 cv = *reinterpret_cast<double2*>(crow + col0 + i);
-              cv.x -= v[i] * (srow * __ldg(g.sb + col0 + i));
-              cv.y -= v[i + 1] * (srow * __ldg(g.sb + col0 + i + 1));
-              *reinterpret_cast<double2*>(crow + col0 + i) = cv;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const long long col = col0 + i;
-              if (col < g.n && (!g.lower || col <= row)) crow[col] -= v[i] * (srow * __ldg(g.sb + col));
-            }
-          }
+          const int cl = 8 * c8 + i;
+          const double sbv = __shfl_sync(0xffffffffu, cl < 32 ? sb_lo : sb_hi, cl & 31);
+          creg[cl] -= h * (srow * sbv);
         }
       }
       tc_fence_before();
-      mbar_arrive(tempty_bar);
+      mbar_arrive(tempty_bar);  // TMEM is free: the MMAs of the next tile start while the stores below drain
       aphase ^= 1u;
+      if (fast) {
+#pragma unroll
+        for (int i = 0; i < OZ_TN; i += 2) *reinterpret_cast<double2*>(crow + i) = make_double2(creg[i], creg[i + 1]);
+      } else if (row_ok) {
+#pragma unroll
+        for (int i = 0; i < OZ_TN; ++i)
+          if (cb + i < g.n && (!g.lower || cb + i <= row)) crow[i] = creg[i];
+      }
+      const long long w2 = clock64();
+      t_wait += w1 - w0;
+      t_busy += w2 - w1;
+    }
+    if (g.dbg && warp == 2 && lane == 0) {
+      g.dbg[blockIdx.x * 8 + 4] = t_wait;
+      g.dbg[blockIdx.x * 8 + 5] = t_busy;
     }
   }
   tc_fence_before();
@@ -420,6 +457,12 @@ extern "C" int ck_oz_split(const double* src, ck_i64 ld, ck_i64 rows, ck_i64 k, 
   ck_oz_split_kernel<<<(unsigned)(rows_pad / 8), 256, 0, ck_stream(stream)>>>(src, ld, rows, (int)k, static_cast<uint8_t*>(fmt_a),
                                                                             static_cast<uint8_t*>(fmt_b), rows_b_pad, scales, vec);
   CK_LAUNCH_CHECK();
+  return CK_OK;
+}
+
+static long long* g_oz_dbg = nullptr;
+extern "C" int ck_oz_debug_buffer(void* dev_counters) {
+  g_oz_dbg = static_cast<long long*>(dev_counters);
   return CK_OK;
 }
 
@@ -462,6 +505,7 @@ extern "C" int ck_oz_gemm(const void* a_slices, const double* sa, ck_i64 m, cons
   const char* e = getenv("CK_OZ_DESC_SWAP");
   g.desc_swap = e ? atoi(e) : 0;
   g.vec = ((((uintptr_t)c) & 15) == 0 && (ldc & 1) == 0) ? 1 : 0;
+  g.dbg = g_oz_dbg;
   long long grid = oz_num_sms();
   if (grid > g.nvirt) grid = g.nvirt;
   ck_oz_gemm_kernel<<<(unsigned)grid, OZ_THREADS, OZ_SMEM, ck_stream(stream)>>>(g);

@@ -94,11 +94,23 @@ def check_case(m, n, k, lower, seed, wide_range=False):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--perf", action="store_true")
+    ap.add_argument("--perf-only", action="store_true", help="skip the checks (profiling runs)")
+    ap.add_argument("--sizes", default="16384x16384xL,32768x32768xL,8832x32768xR")
     ap.add_argument("--out", default=None)
     args = ap.parse_args()
     torch.cuda.set_device(0)
     out = {}
 
+    if not args.perf_only:
+        checks(out)
+    if args.perf or args.perf_only:
+        perf(out, args.sizes)
+    if args.out:
+        with open(args.out, "w") as f:
+            json.dump(out, f, indent=1)
+
+
+def checks(out):
     # 1. digits reconstruct the panel to 2^-56 of the row maximum
     rng = np.random.default_rng(0)
     x = rng.standard_normal((200, 96)) * np.exp(rng.uniform(-20, 5, (200, 1)))
@@ -126,9 +138,14 @@ def main():
         out["cases"].append(r)
         print(json.dumps(r), flush=True)
 
-    if args.perf:
+
+
+def perf(out, sizes):
+    if True:
         out["perf"] = []
-        for (m, n, lower) in [(16384, 16384, True), (32768, 32768, True), (8832, 32768, False)]:
+        for spec in sizes.split(","):
+            ms, ns, ls = spec.split("x")
+            m, n, lower = int(ms), int(ns), ls == "L"
             k = 1024
             a = torch.randn((m, k), dtype=torch.float64, device="cuda")
             b = a if lower else torch.randn((n, k), dtype=torch.float64, device="cuda")
@@ -161,14 +178,20 @@ def main():
             lib.ck_gemm_nt(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), cd.data_ptr(), cd.stride(0), m, n, k, 1, stream())
             e1.record()
             torch.cuda.synchronize()
-            r = {"m": m, "n": n, "k": k, "lower": lower, "split_ms": t_split, "oz_gemm_ms": t_gemm, "oz_TFs_fp64_equiv": flops / t_gemm / 1e9,
+            dbg = torch.zeros(8 * 148, dtype=torch.int64, device="cuda")
+            lib.ck_oz_debug_buffer(dbg.data_ptr())
+            lib.ck_oz_gemm(fa.data_ptr(), sa.data_ptr(), m, fb.data_ptr(), sb.data_ptr(), n, k, c.data_ptr(), c.stride(0), int(lower), stream())
+            torch.cuda.synchronize()
+            lib.ck_oz_debug_buffer(None)
+            d = dbg.cpu().numpy().reshape(148, 8).astype(float)
+            tot = d[:, 0].mean()
+            cyc = {"mma_total_cycles": tot, "mma_wait_operands_frac": d[:, 1].mean() / tot, "mma_wait_tmem_frac": d[:, 2].mean() / tot,
+                   "epi_wait_frac": d[:, 4].mean() / tot, "epi_busy_frac": d[:, 5].mean() / tot}
+            r = {"cycles": cyc, "m": m, "n": n, "k": k, "lower": lower, "split_ms": t_split, "oz_gemm_ms": t_gemm, "oz_TFs_fp64_equiv": flops / t_gemm / 1e9,
                  "dmma_full_rect_ms": e0.elapsed_time(e1), "dmma_TFs": 2.0 * m * n * k / e0.elapsed_time(e1) / 1e9}
             out["perf"].append(r)
             print(json.dumps(r), flush=True)
             del a, b, c, cd, fa, fb
-    if args.out:
-        with open(args.out, "w") as f:
-            json.dump(out, f, indent=1)
 
 
 if __name__ == "__main__":
