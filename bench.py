@@ -263,9 +263,12 @@ def run_gpu(args, n_per_var: int, m: int) -> None:
         ms_per_step = elapsed_ms / args.steps
         value = world * m / (ms_per_step / 1e3)
         wm = work_model(N, m)
-        # dominant kernel: ck_gemm_nt_kernel (DSYRK trailing updates + TRSM updates) = the potrf and solve phases
+        # dominant kernel = the big trailing / solve updates, i.e. the potrf and solve phases (>= 96 % of the step):
+        #   INT8 path (default): ck_oz_gemm_kernel, tcgen05 kind::i8, 28 int8 slice products per FP64 product
+        #   CK_OZAKI=0         : ck_gemm_nt_kernel, FP64 DMMA
         gemm_s = (phase_ms["potrf"] + phase_ms["solve"]) / 1e3
-        achieved_tf = (wm["potrf_flops"] + wm["solve_flops"]) / gemm_s / 1e12
+        fp64_flops = wm["potrf_flops"] + wm["solve_flops"]
+        achieved_tf = fp64_flops / gemm_s / 1e12
         a = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
         b = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
         best = 1e9
@@ -273,12 +276,65 @@ def run_gpu(args, n_per_var: int, m: int) -> None:
             s0, s1 = ev(), ev()
             s0.record(); torch.matmul(a, b); s1.record(); torch.cuda.synchronize()
             best = min(best, s0.elapsed_time(s1))
-        peak_tf = 2 * 8192 ** 3 / best / 1e9
+        dgemm_tf = 2 * 8192 ** 3 / best / 1e9
+        del a, b
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except OSError:
             pass
+        int8_active = bool(_lib.lib.ck_oz_active(N))
+        if int8_active:
+            # isolated launch of the largest update of the factorisation (rows = N - 1024, K = 1024), CUDA events
+            rows, kk = N - 1024, 1024
+            pa = torch.randn((rows, kk), dtype=torch.float64, device="cuda")
+            cc = torch.zeros((rows, ops.padded_ld(rows)), dtype=torch.float64, device="cuda")
+            fa = torch.empty(_lib.lib.ck_oz_slices_bytes(rows, kk, 0), dtype=torch.uint8, device="cuda")
+            fb = torch.empty(_lib.lib.ck_oz_slices_bytes(rows, kk, 1), dtype=torch.uint8, device="cuda")
+            sc = torch.empty(_lib.lib.ck_oz_scales_len(rows), dtype=torch.float64, device="cuda")
+            st = torch.cuda.current_stream().cuda_stream
+            _lib.check(_lib.lib.ck_oz_split(pa.data_ptr(), kk, rows, kk, fa.data_ptr(), fb.data_ptr(), sc.data_ptr(), st))
+            times = []
+            for it in range(5):
+                s0, s1 = ev(), ev()
+                s0.record()
+                _lib.check(_lib.lib.ck_oz_gemm(fa.data_ptr(), sc.data_ptr(), rows, fb.data_ptr(), sc.data_ptr(), rows, kk,
+                                               cc.data_ptr(), cc.stride(0), 1, st))
+                s1.record(); torch.cuda.synchronize()
+                if it >= 2:
+                    times.append(s0.elapsed_time(s1))
+            launch_ms = statistics.mean(times)
+            int8_ops_launch = 28 * 2.0 * kk * rows * (rows + 1) / 2  # algorithmic: lower triangle only
+            del pa, cc, fa, fb, sc
+            bf16_sus, bf16_burst = peaks.get("bf16_tflops_sustained"), peaks.get("bf16_tflops")
+            peak_src = "2 x MEASURED_PEAKS.json bf16_tflops_sustained (int8 dense = 2 x bf16 dense on sm_100a; no int8 figure in the file)"
+            if not bf16_sus:
+                bf16_sus, bf16_burst = 1400.0, 1590.0
+                peak_src = "2 x fallback bf16 sustained 1.4 PFLOP/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)"
+            achieved_int8 = 28 * fp64_flops / gemm_s / 1e12
+            roofline = {
+                "bound": "tensor",
+                "kernel": "ck_oz_gemm_kernel (tcgen05.mma kind::i8, TMEM accumulators): FP64-equivalent trailing / solve updates as 28 "
+                          "int8 slice products per FP64 product",
+                "achieved": achieved_int8, "peak": 2 * bf16_sus, "unit": "TFLOP/s", "frac": achieved_int8 / (2 * bf16_sus),
+                "achieved_note": "int8 tensor ops (2 per MAC) per second over the potrf + solve phases of the timed step, panel chains included",
+                "peak_source": peak_src,
+                "isolated_launch": {"shape": f"lower update, rows={rows}, K={kk}", "ms": launch_ms,
+                                    "int8_TOPs": int8_ops_launch / launch_ms / 1e9,
+                                    "frac_of_2x_bf16_burst": int8_ops_launch / launch_ms / 1e9 / (2 * bf16_burst),
+                                    "fp64_equiv_TFs": int8_ops_launch / 28 / launch_ms / 1e9},
+                "fp64_equiv_TFs": achieved_tf, "dgemm_live_TFs": dgemm_tf, "fp64_equiv_over_dgemm": achieved_tf / dgemm_tf,
+                # ncu --set full of one launch (profiles/r01i_ozgemm_ncu_full_summary.txt: 32768 x 32768 lower, K = 1024):
+                # dram read 17.27 GB + write 4.27 GB; algorithmic 8.59 GB of C + 0.47 GB of slices
+                "traffic": 21.54e9, "traffic_note": "per launch at rows=32768 (ncu), algorithmic 9.06e9",
+                "flops_per_step": fp64_flops}
+        else:
+            roofline = {"bound": "tensor", "kernel": "ck_gemm_nt_kernel (FP64 DMMA: DSYRK trailing + TRSM updates)",
+                        "achieved": achieved_tf, "peak": dgemm_tf, "unit": "TFLOP/s", "frac": achieved_tf / dgemm_tf,
+                        "traffic": None,
+                        "peak_source": "cuBLAS DGEMM 8192^3 measured live in this run (MEASURED_PEAKS.json holds no FP64 figure; "
+                                       f"its hbm_gbs={peaks.get('hbm_gbs')})",
+                        "flops_per_step": fp64_flops}
         line = {
             "metric": METRIC_NAME, "value": value, "unit": "predictions/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -290,12 +346,8 @@ def run_gpu(args, n_per_var: int, m: int) -> None:
             "assembly_GBs": wm["bytes_assembled"] / ((phase_ms["assemble"] + phase_ms["cross"]) / 1e3) / 1e9,
             "cholesky_TFs": wm["potrf_flops"] / (phase_ms["potrf"] / 1e3) / 1e12,
             "solve_TFs": wm["solve_flops"] / (phase_ms["solve"] / 1e3) / 1e12,
-            "roofline": {"bound": "tensor", "kernel": "ck_gemm_nt_kernel (FP64 DMMA: DSYRK trailing + TRSM updates)",
-                         "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                         "traffic": None,
-                         "peak_source": "cuBLAS DGEMM 8192^3 measured live in this run (MEASURED_PEAKS.json holds no FP64 figure; "
-                                        f"its hbm_gbs={peaks.get('hbm_gbs')})",
-                         "flops_per_step": wm["potrf_flops"] + wm["solve_flops"]},
+            "roofline": roofline,
+            "update_path": "int8 tcgen05 (FP64-equivalent)" if int8_active else "fp64 dmma",
             "e2e": {"value": world * m / (e2e_ms / args.steps / 1e3), "unit": "predictions/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
                     "api": "joint_prediction.Predictor.predict_frame (host numpy in, DataFrame out)"},

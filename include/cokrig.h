@@ -274,6 +274,9 @@ int ck_row_dots(const double* v_dev, ck_i64 ldv, ck_i64 nrows, ck_i64 ncols, con
  * these switches. */
 int ck_oz_configure(int enabled, ck_i64 min_rows);
 
+/* 1 if ck_potrf / ck_trsm_lower hand the big updates of an n x n system to the INT8 kernel under the current switches. */
+int ck_oz_active(ck_i64 n);
+
 /* Profiling aid: when set to a device buffer of 8 x 148 int64 counters, every ck_oz_gemm launch stores per-CTA
  * cycle counts there ([0] MMA-issue thread total, [1] waiting for operands, [2] waiting for TMEM, [4] epilogue
  * waiting, [5] epilogue busy).  NULL switches it off (default). */

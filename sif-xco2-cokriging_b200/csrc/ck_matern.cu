@@ -61,7 +61,7 @@ constexpr int K1_THREADS = 256;
 
 // VALUE: 0 = distance only, 1 = covariance
 template <int METRIC, int MODE, int VALUE>
-__global__ void __launch_bounds__(K1_THREADS) ck_block_kernel(const double* __restrict__ xy1, long long n1,
+__global__ void __launch_bounds__(K1_THREADS, 4) ck_block_kernel(const double* __restrict__ xy1, long long n1,
                                                               const double* __restrict__ xy2, long long n2,
                                                               CkMatern P, double* __restrict__ out, long long ld,
                                                               double* __restrict__ out_t, long long ld_t,
@@ -91,8 +91,12 @@ __global__ void __launch_bounds__(K1_THREADS) ck_block_kernel(const double* __re
       const int lc = tx + 32 * c;
       double val = 0.0;
       if (r0 + lr < n1 && c0 + lc < n2) {
-        const double d = ck_dist<METRIC>(pr[lr], pc[lc]);
-        val = VALUE ? ck_matern_cov<MODE>(P, d) : d;
+        if (VALUE && MODE != CK_NU_GENERIC) {  // assembly, closed-form orders: branch-free fast math (ck_math.cuh)
+          val = ck_matern_cov_fast<MODE>(P, ck_dist_fast<METRIC>(pr[lr], pc[lc]));
+        } else {
+          const double d = ck_dist<METRIC>(pr[lr], pc[lc]);
+          val = VALUE ? ck_matern_cov<MODE>(P, d) : d;
+        }
       }
       v[r][c] = val;
     }

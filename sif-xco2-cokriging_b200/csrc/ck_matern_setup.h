@@ -43,12 +43,22 @@ static inline int ck_matern_setup(CkMatern* P, double scale, double nu, double l
   P->len_scale = len_scale;
   P->nu = nu;
   P->sqrt2nu = sqrt(2.0 * nu);
+  P->xscale = P->sqrt2nu / len_scale;
   P->lc = (1.0 - nu) * log(2.0) - lgamma(nu);
   if (nu == 0.5) P->mode = CK_NU_HALF;
   else if (nu == 1.5) P->mode = CK_NU_3HALF;
   else if (nu == 2.5) P->mode = CK_NU_5HALF;
   else if (nu == 3.5) P->mode = CK_NU_7HALF;
   else P->mode = CK_NU_GENERIC;
+  P->x_cut = 1.0e308;
+  if (P->mode != CK_NU_GENERIC) {  // smallest double x at which the reference-order underflow predicate fires
+    double lo = 600.0, hi = 760.0;  // predicate false at lo, true at hi
+    for (int it = 0; it < 200 && nextafter(lo, hi) < hi; ++it) {
+      const double mid = lo + 0.5 * (hi - lo);
+      if (ck_knu_half_underflows(P->mode, mid)) hi = mid; else lo = mid;
+    }
+    P->x_cut = hi;
+  }
   const int nl = (int)(nu + 0.5);
   const long double mu = (long double)nu - (long double)nl;
   const long double m2 = mu * mu;

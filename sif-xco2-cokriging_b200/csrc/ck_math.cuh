@@ -97,6 +97,8 @@ struct CkMatern {
   double nugget;     // added where h == 0 exactly (0 for cross blocks / use_nugget=False)
   double len_scale;  // l
   double sqrt2nu;    // sqrt(2 nu)
+  double xscale;     // sqrt(2 nu) / l   (fast assembly path: x = h * xscale)
+  double x_cut;      // closed-form orders: smallest x with K_nu(x) below the AMOS cut-off (rho flushes to exactly 0 beyond)
   double nu;
   double lc;         // (1 - nu) ln 2 - lgamma(nu)
   // generic-nu constants (Temme): nu = nl + mu, |mu| <= 1/2
@@ -178,6 +180,17 @@ CK_HD double ck_besselk(const CkMatern& P, double x) {
   return rkmu;
 }
 
+// K_nu(x) < AMOS cut-off for the closed-form orders (mode = CK_NU_HALF .. CK_NU_7HALF): scipy's kv returns exactly 0 there
+CK_HD bool ck_knu_half_underflows(int mode, double x) {
+  const double xi = 1.0 / x;
+  double pk;
+  if (mode == CK_NU_HALF) pk = 1.0;
+  else if (mode == CK_NU_3HALF) pk = 1.0 + xi;
+  else if (mode == CK_NU_5HALF) pk = 1.0 + xi * (3.0 + 3.0 * xi);
+  else pk = 1.0 + xi * (6.0 + xi * (15.0 + 15.0 * xi));
+  return sqrt(1.5707963267948966 * xi) * exp(-x) * pk < CK_KV_UNDERFLOW;
+}
+
 // Matern correlation rho(h) with the reference's conventions (src/model.py:354-385).
 template <int MODE>
 CK_HD double ck_matern_corr(const CkMatern& P, double h) {
@@ -195,15 +208,7 @@ CK_HD double ck_matern_corr(const CkMatern& P, double h) {
     else if (MODE == CK_NU_5HALF) poly = 1.0 + x * (1.0 + x * (1.0 / 3.0));
     else poly = 1.0 + x * (1.0 + x * (0.4 + x * (1.0 / 15.0)));
     rho = poly * exp(-x);
-    if (x > 697.0) {  // AMOS underflow guard of scipy.special.kv, applied to K_nu itself
-      const double xi = 1.0 / x;
-      double pk;
-      if (MODE == CK_NU_HALF) pk = 1.0;
-      else if (MODE == CK_NU_3HALF) pk = 1.0 + xi;
-      else if (MODE == CK_NU_5HALF) pk = 1.0 + xi * (3.0 + 3.0 * xi);
-      else pk = 1.0 + xi * (6.0 + xi * (15.0 + 15.0 * xi));
-      if (sqrt(1.5707963267948966 * xi) * exp(-x) * pk < CK_KV_UNDERFLOW) rho = 0.0;
-    }
+    if (x > 697.0 && ck_knu_half_underflows(MODE, x)) rho = 0.0;  // AMOS underflow guard of scipy.special.kv
   }
   if (!(fabs(rho) <= 1.7976931348623157e308)) rho = 0.0;  // non-finite -> 0
   return rho > 0.0 ? rho : 0.0;
@@ -225,4 +230,152 @@ CK_HD double ck_matern_cov_dyn(const CkMatern& P, double h) {
     case CK_NU_7HALF: return ck_matern_cov<CK_NU_7HALF>(P, h);
     default: return ck_matern_cov<CK_NU_GENERIC>(P, h);
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fast, branch-free variants for the covariance-ASSEMBLY kernel (K1, half-integer nu).  The reference-order
+// functions above reproduce the reference's operation order (bit-identical Euclidean distances, libm-level
+// haversine) and are what the distance output, the variogram binning and the local-neighbourhood kernels use.
+// The assembly kernel only owes 1e-12 relative on covariance entries (north star), so it may use range-limited
+// polynomials (coefficients: Chebyshev-node fits generated with mpmath at 60 digits, tools/fit_k1_polys.py),
+// FMA contraction and one Newton-corrected reciprocal square root: ~90 FP64 instructions per haversine +
+// Matern(3/2) entry instead of ~150 with library sin/asin/exp call sequences, and no calls or slow-path branches,
+// so the 16 independent entries of a thread interleave.  Every piece is accurate to <= 2 ulp relative, distances
+// to <= 6e-16 relative (tests/test_hostmath.py), h == 0 exactly for identical points.
+// ------------------------------------------------------------------------------------------------
+#define CK_FMA(a, b, c) fma((a), (b), (c))
+
+// Polynomial coefficients.  On the device they live in constant memory so that every DFMA takes its coefficient
+// as a constant-bank operand; as literals each 64-bit coefficient costs two extra (uniform-datapath) move
+// instructions per use, which made the kernel issue-bound (profiles/r01l K1 notes).
+struct CkFastCoef {
+  double sin_q[8];    // sin(y) = y + y z Q(z), z = y^2, |y| <= pi/2
+  double asin_r[13];  // asin(x) = x (1 + t R(t)), t = x^2 <= 1/4
+  double exp_e[10];   // e^r = 1 + r + r^2 E(r), |r| <= ln2 / 2
+};
+#define CK_FAST_COEF_INIT                                                                                                      \
+  {{-0x1.5555555555555p-3, 0x1.1111111111107p-7, -0x1.a01a01a018aaap-13, 0x1.71de3a54564dfp-19, -0x1.ae6455a1c0795p-26,       \
+    0x1.612401540ed0fp-33, -0x1.ae51366b753a9p-41, 0x1.89a43bea5b135p-49},                                                    \
+   {0x1.5555555555556p-3, 0x1.3333333332ec4p-4, 0x1.6db6db6e3292ep-5, 0x1.f1c71c1d4aa0dp-6, 0x1.6e8bb1d89492bp-6,              \
+    0x1.1c4d343fa57f6p-6, 0x1.c9cf3759fd8ffp-7, 0x1.78246f32d075cp-7, 0x1.524ea8b3aad31p-7, 0x1.653a8f8cfd43cp-8,              \
+    0x1.1d661531b222ep-6, -0x1.e7a24f548c99fp-7, 0x1.d78189767524ep-6},                                                       \
+   {0x1.0000000000001p-1, 0x1.5555555555556p-3, 0x1.5555555553d37p-5, 0x1.11111111109a6p-7, 0x1.6c16c1789d1d7p-10,            \
+    0x1.a01a01a7cebcdp-13, 0x1.a019b8ca26fcfp-16, 0x1.71de0d85293b8p-19, 0x1.2891d4ffbb0f9p-22, 0x1.af390ba7e6f47p-26}}
+#if defined(__CUDACC__)
+static __constant__ CkFastCoef ck_fast_coef_dev = CK_FAST_COEF_INIT;
+#endif
+static const CkFastCoef ck_fast_coef_host = CK_FAST_COEF_INIT;
+#if defined(__CUDA_ARCH__)
+#define CK_COEF(arr, i) (ck_fast_coef_dev.arr[i])
+#else
+#define CK_COEF(arr, i) (ck_fast_coef_host.arr[i])
+#endif
+
+// sin(y) for |y| <= pi/2:  y + y z Q(z), z = y^2, Q of degree 7 (approximation error 0.011 ulp)
+CK_HD double ck_fast_sin(double y) {
+  const double z = y * y;
+  double q = CK_COEF(sin_q, 7);
+#pragma unroll
+  for (int i = 6; i >= 0; --i) q = CK_FMA(q, z, CK_COEF(sin_q, i));
+  return CK_FMA(y * z, q, y);
+}
+
+// sqrt(a) for a >= 0 (a below 1e-300 counts as 0): approximate reciprocal square root + two coupled
+// Goldschmidt steps + one residual correction (<= 1 ulp)
+CK_HD double ck_fast_sqrt(double a) {
+#if defined(__CUDA_ARCH__)
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+  double g = a * r, h = 0.5 * r;
+  double e = fma(-h, g, 0.5);
+  g = fma(g, e, g);
+  h = fma(h, e, h);
+  e = fma(-h, g, 0.5);
+  g = fma(g, e, g);
+  h = fma(h, e, h);
+  g = fma(fma(-g, g, a), h, g);
+  return a > 1.0e-300 ? g : 0.0;
+#else
+  return a > 1.0e-300 ? sqrt(a) : 0.0;
+#endif
+}
+
+// asin(sqrt(a)) for 0 <= a <= 1 without branches.  With R of degree 12, asin(x) = x (1 + x^2 R(x^2)) on |x| <= 1/2:
+//   a <= 1/4        : sqrt(a) (1 + a R(a))
+//   1/4 < a <= 3/4  : pi/4 + u/2 (1 + u^2 R(u^2)),  u = 2a - 1            (asin(sqrt(a)) = pi/4 + asin(2a - 1)/2)
+//   a > 3/4         : pi/2 - sqrt(1 - a) (1 + (1 - a) R(1 - a))
+CK_HD double ck_fast_asin_sqrt(double a) {
+  a = a < 1.0 ? a : 1.0;
+  const bool lo = a <= 0.25, mid = !lo && a <= 0.75;
+  const double om = 1.0 - a, u = CK_FMA(2.0, a, -1.0);
+  const double t = lo ? a : (mid ? u * u : om);
+  const double root = ck_fast_sqrt(lo ? a : om);
+  const double base = lo ? root : (mid ? 0.5 * u : -root);
+  const double off = lo ? 0.0 : (mid ? 0.78539816339744830962 : 1.57079632679489661923);
+  double r = CK_COEF(asin_r, 12);
+#pragma unroll
+  for (int i = 11; i >= 0; --i) r = CK_FMA(r, t, CK_COEF(asin_r, i));
+  return CK_FMA(base, CK_FMA(t, r, 1.0), off);  // off + base (1 + t R(t))
+}
+
+// exp(-x) for 0 <= x <= 700:  2^n e^r, n = rint(-x log2 e), |r| <= ln2 / 2, e^r = 1 + r + r^2 E(r), E of degree 9
+CK_HD double ck_fast_exp_neg(double x) {
+  const double magic = 6755399441055744.0;  // 1.5 * 2^52: the low word of (t + magic) is rint(t) in two's complement
+  const double t = CK_FMA(x, -1.4426950408889634074, magic);
+  const double nf = t - magic;
+  double r = CK_FMA(nf, -6.93147180369123816490e-01, -x);
+  r = CK_FMA(nf, -1.90821492927058770002e-10, r);
+  double e = CK_COEF(exp_e, 9);
+#pragma unroll
+  for (int i = 8; i >= 0; --i) e = CK_FMA(e, r, CK_COEF(exp_e, i));
+  const double p = CK_FMA(r * r, e, r) + 1.0;
+#if defined(__CUDA_ARCH__)
+  const int n = __double2loint(t);
+  return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));  // p in [0.70, 1.42], n >= -1010: normal
+#else
+  return ldexp(p, (int)nf);
+#endif
+}
+
+CK_HD double ck_dist_euclid_fast(const CkPoint& p, const CkPoint& q) {
+  const double dx = p.a - q.a, dy = p.b - q.b;
+  return ck_fast_sqrt(CK_FMA(dx, dx, dy * dy));
+}
+
+// haversine km, branch-free.  sin^2 is even and pi-periodic, so half the longitude difference is reduced by the
+// nearest multiple of pi (two-term pi, exact product for |k| < 2^20); half the latitude difference is within
+// [-pi/2, pi/2] for valid latitudes and goes through the same reduction for safety.
+CK_HD double ck_reduce_pi(double y) {
+  const double magic = 6755399441055744.0;
+  const double k = CK_FMA(y, 0.31830988618379067154, magic) - magic;  // rint(y / pi)
+  return CK_FMA(k, -1.2246467991473532e-16, CK_FMA(k, -3.14159265358979311600, y));
+}
+CK_HD double ck_dist_haversine_fast(const CkPoint& p, const CkPoint& q) {
+  const double s0 = ck_fast_sin(ck_reduce_pi(0.5 * (p.a - q.a)));
+  const double s1 = ck_fast_sin(ck_reduce_pi(0.5 * (p.b - q.b)));
+  const double a = CK_FMA(p.c * q.c, s1 * s1, s0 * s0);
+  return ck_fast_asin_sqrt(a) * (2.0 * CK_EARTH_RADIUS);
+}
+
+template <int METRIC>
+CK_HD double ck_dist_fast(const CkPoint& p, const CkPoint& q) {
+  return METRIC == CK_METRIC_HAVERSINE ? ck_dist_haversine_fast(p, q) : ck_dist_euclid_fast(p, q);
+}
+
+// sigma^2 rho(h) (+ nugget where h == 0) for the closed-form orders nu in {1/2, 3/2, 5/2, 7/2}, branch-free:
+// h == 0 -> sigma^2 + nugget; NaN -> sigma^2 (the reference's `h > 0` mask is False, rho stays 1); x >= x_cut -> 0
+// (scipy's kv underflow flush; x_cut is found on the host by bisecting the reference-order predicate).
+template <int MODE>
+CK_HD double ck_matern_cov_fast(const CkMatern& P, double h) {
+  const double x = fabs(h) * P.xscale;
+  const double xe = x < 705.0 ? x : 705.0;
+  double poly;
+  if (MODE == CK_NU_HALF) poly = 1.0;
+  else if (MODE == CK_NU_3HALF) poly = 1.0 + xe;
+  else if (MODE == CK_NU_5HALF) poly = CK_FMA(xe, CK_FMA(xe, 1.0 / 3.0, 1.0), 1.0);
+  else poly = CK_FMA(xe, CK_FMA(xe, CK_FMA(xe, 1.0 / 15.0, 0.4), 1.0), 1.0);
+  double c = P.scale * (poly * ck_fast_exp_neg(xe));
+  c = x < P.x_cut ? c : 0.0;              // also maps +inf to 0
+  c = x > 0.0 ? c : P.scale;              // x == 0 and NaN: rho = 1
+  return x == 0.0 ? c + P.nugget : c;
 }

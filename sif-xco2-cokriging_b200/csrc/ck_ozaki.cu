@@ -10,7 +10,7 @@
 //   The product panel is   A B^T = s_a s_b sum_g 2^(-8g) G_g ,  G_g = sum_{p+q=g} A_p B_q^T   (int8 x int8 -> int32,
 //   exact: |G_g| <= 7 * 1024 * 2^14 < 2^31).  Groups g = 0..6 are kept (28 slice products); the dropped groups
 //   g >= 7 are zero-mean terms below 2^-56 of (row max) x (column max) per k -- the same order as the FP64
-//   rounding of a DMMA update.  tools/ozaki_sim.py reproduces the scheme in numpy (Cholesky + solve errors
+//   rounding of a DMMA update.  tests/ozaki_model.py reproduces the scheme in numpy (Cholesky + solve errors
 //   equal to LAPACK's to the last digit on the C1 system).
 //
 // Kernel (ck_oz_gemm_kernel, persistent, one CTA per SM, 192 threads, warp-specialised):

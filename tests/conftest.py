@@ -72,6 +72,31 @@ def hostmath():
             lib.ckh_distance(ctypes.c_int(metric), X1.ctypes.data_as(dp), ctypes.c_long(len(X1)), X2.ctypes.data_as(dp),
                              ctypes.c_long(len(X2)), out.ctypes.data_as(dp))
             return out
+
+    def _dist_fast(metric, X1, X2):
+        X1, X2 = np.ascontiguousarray(X1, float), np.ascontiguousarray(X2, float)
+        out = np.empty((len(X1), len(X2)))
+        lib.ckh_distance_fast(ctypes.c_int(metric), X1.ctypes.data_as(dp), ctypes.c_long(len(X1)), X2.ctypes.data_as(dp),
+                              ctypes.c_long(len(X2)), out.ctypes.data_as(dp))
+        return out
+
+    def _matern_fast(scale, nu, ell, nugget, h):
+        h = np.ascontiguousarray(h, float)
+        out = np.empty_like(h)
+        rc = lib.ckh_matern_cov_fast(ctypes.c_double(scale), ctypes.c_double(nu), ctypes.c_double(ell), ctypes.c_double(nugget),
+                                     h.ctypes.data_as(dp), ctypes.c_long(h.size), out.ctypes.data_as(dp))
+        assert rc == 0
+        return out
+
+    def _pieces(x):
+        x = np.ascontiguousarray(x, float)
+        o = [np.empty_like(x) for _ in range(3)]
+        lib.ckh_fast_pieces(x.ctypes.data_as(dp), ctypes.c_long(x.size), *(v.ctypes.data_as(dp) for v in o))
+        return o
+
+    H.distance_fast = staticmethod(_dist_fast)
+    H.matern_cov_fast = staticmethod(_matern_fast)
+    H.fast_pieces = staticmethod(_pieces)
     return H
 
 

@@ -66,3 +66,68 @@ def test_distances(hostmath):
     assert ((d == 0) == (g["hav"] == 0)).all()
     nz = g["hav"] > 0
     assert relerr(d[nz], g["hav"][nz]) < 1e-14
+
+
+# ------------------------------------------------------------------------------------------------
+# fast assembly-path math (K1, closed-form orders): polynomial sin / asin(sqrt) / exp, FMA distances
+def test_fast_pieces_vs_mpmath(hostmath):
+    mp = pytest.importorskip("mpmath")
+    mp.mp.dps = 40
+    rng = np.random.default_rng(2)
+    y = np.concatenate([rng.uniform(-np.pi / 2, np.pi / 2, 1500), 10.0 ** rng.uniform(-12, 0, 500), [np.pi / 2, -np.pi / 2, 0.0]])
+    s, _, _ = hostmath.fast_pieces(y)
+    truth = np.array([float(mp.sin(mp.mpf(float(v)))) for v in y])
+    assert relerr(s[y != 0], truth[y != 0]) < 2.5e-16 and s[-1] == 0.0
+    a = np.concatenate([rng.uniform(0, 1, 1500), 10.0 ** rng.uniform(-30, 0, 500), [0.0, 0.25, 0.75, 1.0, 0.2499999999, 0.7500000001]])
+    _, t, _ = hostmath.fast_pieces(a)
+    truth = np.array([float(mp.asin(mp.sqrt(mp.mpf(float(v))))) for v in a])
+    assert relerr(t[a > 0], truth[a > 0]) < 4.5e-16 and t[a == 0][0] == 0.0
+    x = np.concatenate([rng.uniform(0, 700, 2000), 10.0 ** rng.uniform(-12, 0, 300), [0.0, 690.0, 700.0]])
+    _, _, e = hostmath.fast_pieces(x)
+    truth = np.array([float(mp.exp(-mp.mpf(float(v)))) for v in x])
+    assert relerr(e, truth) < 4.5e-16
+
+
+def test_fast_distances_vs_reference_fixture(hostmath):
+    g = golden("distances")
+    de = hostmath.distance_fast(0, g["Y1"], g["Y2"])
+    assert ((de == 0) == (g["euc"] == 0)).all()
+    assert relerr(de[g["euc"] > 0], g["euc"][g["euc"] > 0]) < 4.5e-16
+    d = hostmath.distance_fast(1, g["X1"], g["X2"])
+    assert ((d == 0) == (g["hav"] == 0)).all()  # h == 0 exactly for identical points: the nugget decision
+    nz = g["hav"] > 0
+    assert relerr(d[nz], g["hav"][nz]) < 2e-15
+    # global pairs incl. the antimeridian fold, poles and antipodes, against the reference-order function
+    rng = np.random.default_rng(5)
+    X = np.c_[rng.uniform(-90, 90, 300), rng.uniform(-180, 180, 300)]
+    X[:4] = [[90, 0], [-90, 10], [0, 180], [0, -180]]
+    a, b = hostmath.distance_fast(1, X, X), hostmath.distance(1, X, X)
+    assert (np.diagonal(a) == 0).all()
+    off = (b > 1e-6) & (b < 19000.0)
+    assert relerr(a[off], b[off]) < 4e-15
+    # within ~1000 km of the antipode asin(sqrt(a)) is ill-conditioned in a (d theta / d a = 1 / (2 sqrt(a (1 - a)))): both
+    # functions carry the 1-2 ulp rounding of a, so they may differ by ~1e-16 / sqrt(1 - a) -- micrometres at most
+    assert np.abs(a - b).max() < 1e-8  # km
+
+
+def test_fast_matern_vs_reference_fixture(hostmath):
+    g = golden("matern")
+    for a, nu in enumerate(g["nus"]):
+        if nu not in (0.5, 1.5, 2.5, 3.5):
+            continue
+        for b, ell in enumerate(g["lens"]):
+            got = hostmath.matern_cov_fast(1.0, nu, ell, 0.0, g["h"])
+            ref = g["corr"][a, b]
+            nz = ref > 0
+            assert relerr(got[nz], ref[nz]) < TOL_COV, (nu, ell)
+            assert ((ref == 0) == (got == 0)).all()
+    for k, nu in enumerate((0.5, 0.82, 1.5, 3.5)):
+        if nu == 0.82:
+            continue
+        got, ref = hostmath.matern_cov_fast(1.0, nu, 0.002, 0.0, g["far_h"]), g["far_corr"][k]
+        assert ((ref == 0) == (got == 0)).all(), nu
+        assert relerr(got[ref > 0], ref[ref > 0]) < TOL_COV
+    h = np.array([0.0, -3.0, np.nan, np.inf])
+    got = hostmath.matern_cov_fast(2.0, 1.5, 10.0, 0.25, h)
+    assert got[0] == 2.25 and got[2] == 2.0 and got[3] == 0.0
+    assert got[1] == pytest.approx(hostmath.matern_cov(2.0, 1.5, 10.0, 0.25, h)[1], rel=1e-15)
