@@ -299,6 +299,13 @@ int ck_oz_split(const double* src_dev, ck_i64 ld, ck_i64 rows, ck_i64 k, void* f
 int ck_oz_gemm(const void* a_slices_dev, const double* a_scales_dev, ck_i64 m, const void* b_slices_dev,
                const double* b_scales_dev, ck_i64 n, ck_i64 k, double* c_dev, ck_i64 ldc, int lower, void* stream);
 
+/* The same product with the masking contract of ck_mg_update: C is the local part of a 2-D block-cyclic matrix (square
+ * tiles of tb elements, local tile (li, lj) = global tile (row_tile0 + li row_tile_step, col_tile0 + lj col_tile_step));
+ * tiles with J > I are skipped, tiles with J == I keep their lower triangle.  m, n whole tiles. */
+int ck_oz_mg_update(const void* a_slices_dev, const double* a_scales_dev, ck_i64 m, const void* b_slices_dev,
+                    const double* b_scales_dev, ck_i64 n, ck_i64 k, double* c_dev, ck_i64 ldc, ck_i64 tb, ck_i64 row_tile0,
+                    ck_i64 row_tile_step, ck_i64 col_tile0, ck_i64 col_tile_step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

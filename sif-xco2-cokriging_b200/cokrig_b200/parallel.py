@@ -228,8 +228,31 @@ class CudaKernels:
         self.check(self.lib.ck_trsm_lower(o._ptr(pack), tb, tb, o._ptr(pack[tb * tb:]), o._ptr(rows), rows.shape[0],
                                           rows.stride(0), o._stream()), "ck_trsm_lower")
 
+    def _oz_scratch(self, rows_a: int, rows_b: int, k: int):
+        """Slice / scale buffers of the INT8 update path, grown on demand and reused (main stream only)."""
+        need = (int(self.lib.ck_oz_slices_bytes(rows_a, k, 0)), int(self.lib.ck_oz_slices_bytes(rows_b, k, 1)),
+                int(self.lib.ck_oz_scales_len(rows_a)), int(self.lib.ck_oz_scales_len(rows_b)))
+        have = getattr(self, "_oz", None)
+        if have is None or any(h.numel() < n for h, n in zip(have, need)):
+            self._oz = (self.empty(need[0], dtype=torch.uint8), self.empty(need[1], dtype=torch.uint8),
+                        self.empty(need[2]), self.empty(need[3]))
+        return self._oz
+
     def update(self, A, B, C, tb, gi0, gis, gj0, gjs) -> None:
         o = self.ops
+        m, n, k = C.shape[0], C.shape[1], A.shape[1]
+        # ck_oz_active(2 min(m, n)): the INT8 path is on and min(m, n) >= max(1024, its smallest-dimension switch)
+        if (k % 32 == 0 and k <= 1024 and self.lib.ck_oz_active(2 * min(m, n))
+                and torch.cuda.current_stream(self.device) == self.main):
+            # big trailing updates on the INT8 tensor cores (FP64-equivalent, csrc/ck_ozaki.cu): split both panels into
+            # digit slices, then one persistent tcgen05 kernel with the block-cyclic mask
+            fa, fb, sa, sb = self._oz_scratch(m, n, k)
+            st = o._stream()
+            self.check(self.lib.ck_oz_split(o._ptr(A), A.stride(0), m, k, o._ptr(fa), None, o._ptr(sa), st), "ck_oz_split")
+            self.check(self.lib.ck_oz_split(o._ptr(B), B.stride(0), n, k, None, o._ptr(fb), o._ptr(sb), st), "ck_oz_split")
+            self.check(self.lib.ck_oz_mg_update(o._ptr(fa), o._ptr(sa), m, o._ptr(fb), o._ptr(sb), n, k, o._ptr(C), C.stride(0),
+                                                tb, gi0, gis, gj0, gjs, st), "ck_oz_mg_update")
+            return
         self.check(self.lib.ck_mg_update(o._ptr(A), A.stride(0), o._ptr(B), B.stride(0), o._ptr(C), C.stride(0), C.shape[0],
                                          C.shape[1], A.shape[1], tb, gi0, gis, gj0, gjs, o._stream()), "ck_mg_update")
 

@@ -61,7 +61,7 @@ constexpr int K1_THREADS = 256;
 
 // VALUE: 0 = distance only, 1 = covariance
 template <int METRIC, int MODE, int VALUE>
-__global__ void __launch_bounds__(K1_THREADS, 4) ck_block_kernel(const double* __restrict__ xy1, long long n1,
+__global__ void __launch_bounds__(K1_THREADS, (MODE == CK_NU_GENERIC && VALUE) ? 2 : 4) ck_block_kernel(const double* __restrict__ xy1, long long n1,
                                                               const double* __restrict__ xy2, long long n2,
                                                               CkMatern P, double* __restrict__ out, long long ld,
                                                               double* __restrict__ out_t, long long ld_t,

@@ -223,6 +223,11 @@ struct OzGemmArgs {
   int lower;          // 1: only entries with col <= row are updated (tiles above the diagonal are skipped)
   int tri;            // 1: triangular virtual tile space (square lower update), 0: rectangular
   long long nvirt;    // virtual tiles
+  // block-cyclic mode (tb > 0): C is the local part of a 2-D block-cyclic matrix with square tiles of tb elements; local
+  // tile (li, lj) is global tile (gi0 + li gis, gj0 + lj gjs); tiles with J > I are skipped, tiles with J == I keep
+  // their lower triangle (same contract as ck_mg_update)
+  int tb;
+  long long gi0, gis, gj0, gjs;
   int desc_swap;      // debug: exchange LBO / SBO
   int vec;            // C is 16-byte aligned with an even leading dimension
   long long* dbg;     // optional per-CTA cycle counters (8 per CTA), see ck_oz_debug_buffer
@@ -244,7 +249,24 @@ __device__ __forceinline__ bool oz_decode(const OzGemmArgs& g, long long t, int&
   }
   j = (int)(u >> 3);
   I = (int)(8 * s + (u & 7));
-  return I < g.ni && j < g.nj && (!g.lower || j <= 2 * I + 1);
+  if (I >= g.ni || j >= g.nj) return false;
+  if (g.tb) {
+    const long long li = ((long long)I * OZ_TM) / g.tb, lj = ((long long)j * OZ_TN) / g.tb;
+    const long long Ig = g.gi0 + li * g.gis, Jg = g.gj0 + lj * g.gjs;
+    if (Jg > Ig) return false;
+    return Jg < Ig || ((long long)j * OZ_TN - lj * g.tb) <= ((long long)I * OZ_TM + OZ_TM - 1 - li * g.tb);
+  }
+  return !g.lower || j <= 2 * I + 1;
+}
+
+// largest column of C that row `row` may update inside column block j (LLONG_MAX: no mask)
+__device__ __forceinline__ long long oz_col_limit(const OzGemmArgs& g, long long row, int j) {
+  if (g.tb) {
+    const long long li = row / g.tb, lj = ((long long)j * OZ_TN) / g.tb;
+    const long long Ig = g.gi0 + li * g.gis, Jg = g.gj0 + lj * g.gjs;
+    return Jg == Ig ? lj * g.tb + (row - li * g.tb) : 0x7fffffffffffffffLL;
+  }
+  return g.lower ? row : 0x7fffffffffffffffLL;
 }
 
 __global__ void __launch_bounds__(OZ_THREADS, 1) ck_oz_gemm_kernel(OzGemmArgs g) {
@@ -370,7 +392,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ck_oz_gemm_kernel(OzGemmArgs g)
       double* crow = g.c + (row_ok ? row : 0) * g.ldc + cb;
       const double sb_lo = (cb + lane < g.n) ? __ldg(g.sb + cb + lane) : 0.0;
       const double sb_hi = (cb + 32 + lane < g.n) ? __ldg(g.sb + cb + 32 + lane) : 0.0;
-      const bool fast = g.vec && row_ok && (cb + OZ_TN - 1 < g.n) && (!g.lower || cb + OZ_TN - 1 <= row);
+      const long long clim = oz_col_limit(g, row_ok ? row : 0, j);
+      const bool fast = g.vec && row_ok && (cb + OZ_TN - 1 < g.n) && (cb + OZ_TN - 1 <= clim);
       double creg[OZ_TN];
       if (fast) {
 #pragma unroll
@@ -382,7 +405,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ck_oz_gemm_kernel(OzGemmArgs g)
       } else {
 #pragma unroll
         for (int i = 0; i < OZ_TN; ++i)
-          creg[i] = (row_ok && cb + i < g.n && (!g.lower || cb + i <= row)) ? crow[i] : 0.0;
+          creg[i] = (row_ok && cb + i < g.n && cb + i <= clim) ? crow[i] : 0.0;
       }
       const long long w0 = clock64();
       mbar_wait(tfull_bar, aphase);
@@ -414,7 +437,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ck_oz_gemm_kernel(OzGemmArgs g)
       } else if (row_ok) {
 #pragma unroll
         for (int i = 0; i < OZ_TN; ++i)
-          if (cb + i < g.n && (!g.lower || cb + i <= row)) crow[i] = creg[i];
+          if (cb + i < g.n && cb + i <= clim) crow[i] = creg[i];
       }
       const long long w2 = clock64();
       t_wait += w1 - w0;
@@ -476,8 +499,9 @@ static int oz_num_sms() {
   return v;
 }
 
-extern "C" int ck_oz_gemm(const void* a_slices, const double* sa, ck_i64 m, const void* b_slices, const double* sb, ck_i64 n,
-                          ck_i64 k, double* c, ck_i64 ldc, int lower, void* stream) {
+static int oz_gemm_launch(const void* a_slices, const double* sa, ck_i64 m, const void* b_slices, const double* sb, ck_i64 n,
+                          ck_i64 k, double* c, ck_i64 ldc, int lower, ck_i64 tb, ck_i64 gi0, ck_i64 gis, ck_i64 gj0, ck_i64 gjs,
+                          void* stream) {
   CK_REQUIRE(m >= 0 && n >= 0 && k >= 0, "negative size");
   if (m == 0 || n == 0 || k == 0) return CK_OK;
   CK_REQUIRE(a_slices && b_slices && sa && sb && c, "null pointer");
@@ -496,7 +520,8 @@ extern "C" int ck_oz_gemm(const void* a_slices, const double* sa, ck_i64 m, cons
   g.kcn = (int)(k / OZ_KC);
   g.ni = (int)((m + OZ_TM - 1) / OZ_TM);
   g.nj = (int)((n + OZ_TN - 1) / OZ_TN);
-  g.lower = lower ? 1 : 0;
+  g.lower = (lower && !tb) ? 1 : 0;
+  g.tb = (int)tb; g.gi0 = gi0; g.gis = gis; g.gj0 = gj0; g.gjs = gjs;
   const long long srows = (g.ni + 7) / 8;
   // the triangular tile space needs every super-row s to hold its 16 s + 16 column blocks; use it for (near-)square
   // lower updates, the rectangular space otherwise
@@ -511,4 +536,19 @@ extern "C" int ck_oz_gemm(const void* a_slices, const double* sa, ck_i64 m, cons
   ck_oz_gemm_kernel<<<(unsigned)grid, OZ_THREADS, OZ_SMEM, ck_stream(stream)>>>(g);
   CK_LAUNCH_CHECK();
   return CK_OK;
+}
+
+extern "C" int ck_oz_gemm(const void* a_slices, const double* sa, ck_i64 m, const void* b_slices, const double* sb, ck_i64 n,
+                          ck_i64 k, double* c, ck_i64 ldc, int lower, void* stream) {
+  return oz_gemm_launch(a_slices, sa, m, b_slices, sb, n, k, c, ldc, lower, 0, 0, 1, 0, 1, stream);
+}
+
+extern "C" int ck_oz_mg_update(const void* a_slices, const double* sa, ck_i64 m, const void* b_slices, const double* sb, ck_i64 n,
+                               ck_i64 k, double* c, ck_i64 ldc, ck_i64 tb, ck_i64 row_tile0, ck_i64 row_tile_step, ck_i64 col_tile0,
+                               ck_i64 col_tile_step, void* stream) {
+  CK_REQUIRE(tb > 0 && tb % 128 == 0, "tile size must be a multiple of 128 (got %lld)", (long long)tb);
+  CK_REQUIRE(m % tb == 0 && n % tb == 0, "m and n must be whole tiles");
+  CK_REQUIRE(row_tile_step >= 1 && col_tile_step >= 1 && row_tile0 >= 0 && col_tile0 >= 0, "bad tile map");
+  return oz_gemm_launch(a_slices, sa, m, b_slices, sb, n, k, c, ldc, 0, tb, row_tile0, row_tile_step, col_tile0, col_tile_step,
+                        stream);
 }

@@ -50,6 +50,30 @@ def test_block_cyclic_single_rank_vs_oracle(metric, params, tile, lookahead):
     assert abs(solver.logdet() / np.linalg.slogdet(sigma)[1] - 1) < 1e-10
 
 
+def test_block_cyclic_single_rank_int8_updates_vs_oracle():
+    """The same sweep with the trailing updates on the INT8 tensor cores (ck_oz_split + ck_oz_mg_update)."""
+    from cokrig_b200 import parallel
+    from cokrig_b200._lib import lib
+    coords, z, targets = _inputs(0, 1500, 1400, 600, 23)
+    lib.ck_oz_configure(1, 256)
+    try:
+        launches0 = lib.ck_launch_count()
+        solver = parallel.BlockCyclicCokriging(parallel.ProcessGrid(1, 1), tile=256, lookahead=True)
+        pred, var, info = solver.solve(coords, z, targets, HALF, 2, 1, 0)
+        n_int8 = lib.ck_launch_count() - launches0
+        lib.ck_oz_configure(0, -1)
+        launches0 = lib.ck_launch_count()
+        pred_d, var_d, _ = parallel.BlockCyclicCokriging(parallel.ProcessGrid(1, 1), tile=256).solve(coords, z, targets, HALF, 2, 1, 0)
+        n_dmma = lib.ck_launch_count() - launches0
+    finally:
+        lib.ck_oz_configure(1, 4096)
+    rp, re, _ = orc.joint_predict(orc.Params(HALF), 1, coords, z, targets, "euclidean")
+    assert info == 0 and n_int8 > n_dmma  # the INT8 path launches two splits + one product per big update
+    assert np.max(np.abs(pred - rp)) / np.max(np.abs(rp)) < 1e-9
+    assert np.max(np.abs(var - re ** 2)) < 1e-9
+    assert np.max(np.abs(pred - pred_d)) / np.max(np.abs(rp)) < 1e-11
+
+
 def test_block_cyclic_single_rank_reports_non_pd():
     from cokrig_b200 import parallel
     coords, z, targets = _inputs(0, 300, 280, 20, 2)
