@@ -13,7 +13,7 @@
 //   rounding of a DMMA update.  tests/ozaki_model.py reproduces the scheme in numpy (Cholesky + solve errors
 //   equal to LAPACK's to the last digit on the C1 system).
 //
-// Kernel (ck_oz_gemm_kernel, persistent, one CTA per SM, 192 threads, warp-specialised):
+// Kernel (ck_oz_gemm_kernel, persistent, one CTA per SM, 320 threads, warp-specialised):
 //   CTA tile 128 (rows of A) x 64 (rows of B); ALL seven group accumulators live in TMEM at once
 //   (7 x 64 = 448 of 512 columns), so every operand byte is fetched once per tile and the FP64 epilogue runs
 //   once per tile (K = 1024 deep), not once per group.
@@ -25,7 +25,7 @@
 //                      in shared memory with the row-group stride of one slice, so A_p x [B_q..B_q+3] is ONE
 //                      M=128, N=256 instruction whose 256 accumulator columns are exactly the group blocks
 //                      p+q..p+q+3 (A is read 10 times per chunk instead of 28).
-//   warps 2-5 epilogue: tcgen05.ld the 7 int32 group blocks, Horner in FP64 (v = v 2^-8 + G_g, exact
+//   warps 2-9 epilogue: tcgen05.ld the 7 int32 group blocks, Horner in FP64 (v = v 2^-8 + G_g, exact
 //                      conversions), scale by s_a s_b (powers of two: exact) and C -= v.
 #include <stdint.h>
 #include <stdlib.h>
@@ -43,7 +43,8 @@ constexpr int OZ_B_KU = OZ_S * OZ_TN * 16;     // 7168 B:  [q 7][row group 8][ro
 constexpr int OZ_B_STAGE = 2 * OZ_B_KU;        // 14336 B: [ku 2][...]
 constexpr int OZ_STAGE = OZ_A_STAGE + OZ_B_STAGE;
 constexpr int OZ_NSTAGE = 4;
-constexpr int OZ_THREADS = 192;
+constexpr int OZ_EPI_WARPS = 8;                // 2 per TMEM lane quadrant, 32 columns each
+constexpr int OZ_THREADS = 64 + 32 * OZ_EPI_WARPS;
 constexpr int OZ_TMEM_COLS = 512;
 constexpr size_t OZ_SMEM = (size_t)OZ_NSTAGE * OZ_STAGE + 1024 /* alignment slack */ + 256 /* barriers */;
 
@@ -228,7 +229,6 @@ struct OzGemmArgs {
   // their lower triangle (same contract as ck_mg_update)
   int tb;
   long long gi0, gis, gj0, gjs;
-  int desc_swap;      // debug: exchange LBO / SBO
   int vec;            // C is 16-byte aligned with an even leading dimension
   long long* dbg;     // optional per-CTA cycle counters (8 per CTA), see ck_oz_debug_buffer
 };
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ck_oz_gemm_kernel(OzGemmArgs g)
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(tfull_bar, 1);
-    mbar_init(tempty_bar, 128);
+    mbar_init(tempty_bar, 32 * OZ_EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -330,8 +330,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ck_oz_gemm_kernel(OzGemmArgs g)
       uint32_t phase = 0, aphase = 0;
       long long t_full = 0, t_tempty = 0;
       const long long t_start = clock64();
-      const uint32_t a_lbo = g.desc_swap ? 128u : 2048u, a_sbo = g.desc_swap ? 2048u : 128u;
-      const uint32_t b_lbo = g.desc_swap ? 128u : (uint32_t)OZ_B_KU, b_sbo = g.desc_swap ? (uint32_t)OZ_B_KU : 128u;
+      const uint32_t a_lbo = 2048u, a_sbo = 128u;                // A slice: [ku][row group][8 rows][16 B]
+      const uint32_t b_lbo = (uint32_t)OZ_B_KU, b_sbo = 128u;   // B k-unit: [q][row group][8 rows][16 B]
       const uint32_t id256 = umma_idesc_i8(256), id192 = umma_idesc_i8(192), id128 = umma_idesc_i8(128), id64 = umma_idesc_i8(64);
       for (long long t = blockIdx.x; t < g.nvirt; t += gridDim.x) {
         int I, j;
@@ -375,36 +375,37 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ck_oz_gemm_kernel(OzGemmArgs g)
     }
     __syncwarp();
   } else {
-    // ===== epilogue: warps 2..5 own TMEM lane quadrants (warp % 4); a thread owns one row x 64 columns =====
+    // ===== epilogue: warps 2..9; warp w reads TMEM lane quadrant w % 4, column half (w - 2) / 4; a thread owns one
+    // row x 32 columns =====
     // The C row segment is loaded BEFORE waiting for the accumulators (its latency hides behind the MMAs of the
     // tile), TMEM is released as soon as the last block has been read, and the stores are issued after that, so
     // only TMEM reads + the FP64 recombination sit between two tiles of the MMA stream.
-    const int qd = warp & 3;
+    constexpr int EC = OZ_TN / (OZ_EPI_WARPS / 4);  // columns per thread
+    const int qd = warp & 3, half = (warp - 2) >> 2;
     uint32_t aphase = 0;
     long long t_busy = 0, t_wait = 0;
     for (long long t = blockIdx.x; t < g.nvirt; t += gridDim.x) {
       int I, j;
       if (!oz_decode(g, t, I, j)) continue;
       const long long row = (long long)I * OZ_TM + 32 * qd + lane;
-      const long long cb = (long long)j * OZ_TN;
+      const long long cb = (long long)j * OZ_TN + EC * half;
       const bool row_ok = row < g.m;
       const double srow = row_ok ? g.sa[row] : 0.0;
       double* crow = g.c + (row_ok ? row : 0) * g.ldc + cb;
-      const double sb_lo = (cb + lane < g.n) ? __ldg(g.sb + cb + lane) : 0.0;
-      const double sb_hi = (cb + 32 + lane < g.n) ? __ldg(g.sb + cb + 32 + lane) : 0.0;
+      const double sb_l = (cb + lane < g.n) ? __ldg(g.sb + cb + lane) : 0.0;
       const long long clim = oz_col_limit(g, row_ok ? row : 0, j);
-      const bool fast = g.vec && row_ok && (cb + OZ_TN - 1 < g.n) && (cb + OZ_TN - 1 <= clim);
-      double creg[OZ_TN];
+      const bool fast = g.vec && row_ok && (cb + EC - 1 < g.n) && (cb + EC - 1 <= clim);
+      double creg[EC];
       if (fast) {
 #pragma unroll
-        for (int i = 0; i < OZ_TN; i += 2) {
+        for (int i = 0; i < EC; i += 2) {
           const double2 cv = *reinterpret_cast<const double2*>(crow + i);
           creg[i] = cv.x;
           creg[i + 1] = cv.y;
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < OZ_TN; ++i)
+        for (int i = 0; i < EC; ++i)
           creg[i] = (row_ok && cb + i < g.n && cb + i <= clim) ? crow[i] : 0.0;
       }
       const long long w0 = clock64();
@@ -412,9 +413,9 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ck_oz_gemm_kernel(OzGemmArgs g)
       tc_fence_after();
       const long long w1 = clock64();
 #pragma unroll
-      for (int c8 = 0; c8 < OZ_TN / 8; ++c8) {
+      for (int c8 = 0; c8 < EC / 8; ++c8) {
         int acc[OZ_S][8];
-        const uint32_t taddr = tmem + ((uint32_t)(32 * qd) << 16) + (uint32_t)(8 * c8);
+        const uint32_t taddr = tmem + ((uint32_t)(32 * qd) << 16) + (uint32_t)(EC * half + 8 * c8);
 #pragma unroll
         for (int gb = 0; gb < OZ_S; ++gb) tc_ld8(taddr + (uint32_t)(gb * OZ_TN), acc[gb]);
         tc_wait_ld();
@@ -424,7 +425,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ck_oz_gemm_kernel(OzGemmArgs g)
 #pragma unroll
           for (int gb = OZ_S - 2; gb >= 0; --gb) h = fma(h, 0.00390625, (double)acc[gb][i]);
           const int cl = 8 * c8 + i;
-          const double sbv = __shfl_sync(0xffffffffu, cl < 32 ? sb_lo : sb_hi, cl & 31);
+          const double sbv = __shfl_sync(0xffffffffu, sb_l, cl);
           creg[cl] -= h * (srow * sbv);
         }
       }
@@ -433,10 +434,10 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ck_oz_gemm_kernel(OzGemmArgs g)
       aphase ^= 1u;
       if (fast) {
 #pragma unroll
-        for (int i = 0; i < OZ_TN; i += 2) *reinterpret_cast<double2*>(crow + i) = make_double2(creg[i], creg[i + 1]);
+        for (int i = 0; i < EC; i += 2) *reinterpret_cast<double2*>(crow + i) = make_double2(creg[i], creg[i + 1]);
       } else if (row_ok) {
 #pragma unroll
-        for (int i = 0; i < OZ_TN; ++i)
+        for (int i = 0; i < EC; ++i)
           if (cb + i < g.n && cb + i <= clim) crow[i] = creg[i];
       }
       const long long w2 = clock64();
@@ -527,8 +528,6 @@ static int oz_gemm_launch(const void* a_slices, const double* sa, ck_i64 m, cons
   // lower updates, the rectangular space otherwise
   g.tri = (g.lower && (long long)g.nj >= 2LL * g.ni - 1) ? 1 : 0;
   g.nvirt = g.tri ? 64 * srows * (srows + 1) : srows * 8LL * g.nj;
-  const char* e = getenv("CK_OZ_DESC_SWAP");
-  g.desc_swap = e ? atoi(e) : 0;
   g.vec = ((((uintptr_t)c) & 15) == 0 && (ldc & 1) == 0) ? 1 : 0;
   g.dbg = g_oz_dbg;
   long long grid = oz_num_sms();
