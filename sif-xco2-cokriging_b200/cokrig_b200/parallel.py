@@ -21,6 +21,7 @@ partitioning, communication order and reductions without a GPU.
 from __future__ import annotations
 
 import contextlib
+import os
 from typing import Callable, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -222,36 +223,63 @@ class CudaKernels:
                    "ck_potrf")
         pack[: tb * tb].view(tb, tb).copy_(tile)
 
-    def trsm(self, pack: torch.Tensor, tb: int, rows: torch.Tensor) -> None:
-        """rows <- rows L^-T for the (nrows x tb) view `rows` (row stride = its leading dimension)."""
-        o = self.ops
-        self.check(self.lib.ck_trsm_lower(o._ptr(pack), tb, tb, o._ptr(pack[tb * tb:]), o._ptr(rows), rows.shape[0],
-                                          rows.stride(0), o._stream()), "ck_trsm_lower")
+    # INT8 tensor-core path (FP64-equivalent products, csrc/ck_ozaki.cu) ---------------------------
+    def _int8_ok(self, m: int, n: int, k: int) -> bool:
+        """Worth a persistent tcgen05 launch: path enabled, K in range, enough 128 x 64 tiles to fill the machine."""
+        min_tiles = int(os.environ.get("CK_MG_INT8_MIN_TILES", "600"))
+        return bool(self.lib.ck_oz_active(1 << 20)) and k % 32 == 0 and 256 <= k <= 1024 and (m // 128) * (n // 64) >= min_tiles
 
     def _oz_scratch(self, rows_a: int, rows_b: int, k: int):
-        """Slice / scale buffers of the INT8 update path, grown on demand and reused (main stream only)."""
+        """Slice / scale buffers, one set per stream (main / panel), grown on demand and reused."""
         need = (int(self.lib.ck_oz_slices_bytes(rows_a, k, 0)), int(self.lib.ck_oz_slices_bytes(rows_b, k, 1)),
                 int(self.lib.ck_oz_scales_len(rows_a)), int(self.lib.ck_oz_scales_len(rows_b)))
-        have = getattr(self, "_oz", None)
+        if not hasattr(self, "_oz"):
+            self._oz = {}
+        key = torch.cuda.current_stream(self.device).cuda_stream
+        have = self._oz.get(key)
         if have is None or any(h.numel() < n for h, n in zip(have, need)):
-            self._oz = (self.empty(need[0], dtype=torch.uint8), self.empty(need[1], dtype=torch.uint8),
-                        self.empty(need[2]), self.empty(need[3]))
-        return self._oz
+            self._oz[key] = have = (self.empty(need[0], dtype=torch.uint8), self.empty(need[1], dtype=torch.uint8),
+                                    self.empty(need[2]), self.empty(need[3]))
+        return have
+
+    def _oz_product(self, A, B, C, tb=0, gi0=0, gis=1, gj0=0, gjs=1) -> None:
+        """C -= A B^T through digit slices; tb > 0: block-cyclic mask of ck_mg_update."""
+        o = self.ops
+        m, n, k = A.shape[0], B.shape[0], A.shape[1]
+        fa, fb, sa, sb = self._oz_scratch(m, n, k)
+        st = o._stream()
+        self.check(self.lib.ck_oz_split(o._ptr(A), A.stride(0), m, k, o._ptr(fa), None, o._ptr(sa), st), "ck_oz_split")
+        self.check(self.lib.ck_oz_split(o._ptr(B), B.stride(0), n, k, None, o._ptr(fb), o._ptr(sb), st), "ck_oz_split")
+        if tb:
+            self.check(self.lib.ck_oz_mg_update(o._ptr(fa), o._ptr(sa), m, o._ptr(fb), o._ptr(sb), n, k, o._ptr(C), C.stride(0),
+                                                tb, gi0, gis, gj0, gjs, st), "ck_oz_mg_update")
+        else:
+            self.check(self.lib.ck_oz_gemm(o._ptr(fa), o._ptr(sa), m, o._ptr(fb), o._ptr(sb), n, k, o._ptr(C), C.stride(0), 0, st),
+                       "ck_oz_gemm")
+
+    def trsm(self, pack: torch.Tensor, tb: int, rows: torch.Tensor, out: torch.Tensor) -> None:
+        """rows <- rows L^-T for the (nrows x tb) view `rows` (row stride = its leading dimension); `out` (nrows x tb,
+        contiguous) receives a copy of the result (the panel staging buffer)."""
+        o = self.ops
+        nrows = rows.shape[0]
+        if self._int8_ok(nrows, tb, tb):
+            # one INT8 product with the explicitly inverted tile: X^T = solve(L, I) (target-major), rows L^-T = rows (X)^T
+            xt = torch.eye(tb, dtype=F64, device=self.device)
+            self.check(self.lib.ck_trsm_lower(o._ptr(pack), tb, tb, o._ptr(pack[tb * tb:]), o._ptr(xt), tb, tb, o._stream()),
+                       "ck_trsm_lower")
+            negx = (-xt).t().contiguous()      # row j = -(row j of L^-1)
+            out.zero_()
+            self._oz_product(rows, negx, out)  # out = 0 - rows (-X)^T
+            rows.copy_(out)
+            return
+        self.check(self.lib.ck_trsm_lower(o._ptr(pack), tb, tb, o._ptr(pack[tb * tb:]), o._ptr(rows), nrows,
+                                          rows.stride(0), o._stream()), "ck_trsm_lower")
+        out.copy_(rows)
 
     def update(self, A, B, C, tb, gi0, gis, gj0, gjs) -> None:
         o = self.ops
-        m, n, k = C.shape[0], C.shape[1], A.shape[1]
-        # ck_oz_active(2 min(m, n)): the INT8 path is on and min(m, n) >= max(1024, its smallest-dimension switch)
-        if (k % 32 == 0 and k <= 1024 and self.lib.ck_oz_active(2 * min(m, n))
-                and torch.cuda.current_stream(self.device) == self.main):
-            # big trailing updates on the INT8 tensor cores (FP64-equivalent, csrc/ck_ozaki.cu): split both panels into
-            # digit slices, then one persistent tcgen05 kernel with the block-cyclic mask
-            fa, fb, sa, sb = self._oz_scratch(m, n, k)
-            st = o._stream()
-            self.check(self.lib.ck_oz_split(o._ptr(A), A.stride(0), m, k, o._ptr(fa), None, o._ptr(sa), st), "ck_oz_split")
-            self.check(self.lib.ck_oz_split(o._ptr(B), B.stride(0), n, k, None, o._ptr(fb), o._ptr(sb), st), "ck_oz_split")
-            self.check(self.lib.ck_oz_mg_update(o._ptr(fa), o._ptr(sa), m, o._ptr(fb), o._ptr(sb), n, k, o._ptr(C), C.stride(0),
-                                                tb, gi0, gis, gj0, gjs, st), "ck_oz_mg_update")
+        if self._int8_ok(C.shape[0], C.shape[1], A.shape[1]):
+            self._oz_product(A, B, C, tb, gi0, gis, gj0, gjs)
             return
         self.check(self.lib.ck_mg_update(o._ptr(A), A.stride(0), o._ptr(B), B.stride(0), o._ptr(C), C.stride(0), C.shape[0],
                                          C.shape[1], A.shape[1], tb, gi0, gis, gj0, gjs, o._stream()), "ck_mg_update")
@@ -453,8 +481,7 @@ class BlockCyclicCokriging:
                 li0 = first_local_after(k, P, p)
                 if li0 < self.LRt:
                     rows = local[li0 * tb: self.LRt * tb, ljk * tb:(ljk + 1) * tb]
-                    K.trsm(pack, tb, rows)
-                    stage_b[p, li0: self.LRt].view(-1, tb).copy_(rows)
+                    K.trsm(pack, tb, rows, stage_b[p, li0: self.LRt].view(-1, tb))
             if g.world > 1:
                 for pp in range(P):
                     l0, l1 = first_local_after(k, P, pp), local_tiles(self.TR, P, pp)

@@ -89,10 +89,11 @@ class NumpyKernels:
         t[il] = L[il]  # the upper triangle is left untouched, like ck_potrf
         pack[: tb * tb].view(tb, tb).copy_(torch.from_numpy(np.ascontiguousarray(L)))
 
-    def trsm(self, pack, tb, rows):
+    def trsm(self, pack, tb, rows, out):
         L = pack[: tb * tb].view(tb, tb).numpy()
         r = rows.numpy()
         r[...] = np.linalg.solve(np.tril(L), r.T).T
+        out.copy_(rows)
 
     def update(self, A, B, C, tb, gi0, gis, gj0, gjs):
         a, b, c = A.numpy(), B.numpy(), C.numpy()

@@ -55,7 +55,7 @@ def test_block_cyclic_single_rank_int8_updates_vs_oracle():
     from cokrig_b200 import parallel
     from cokrig_b200._lib import lib
     coords, z, targets = _inputs(0, 1500, 1400, 600, 23)
-    lib.ck_oz_configure(1, 256)
+    os.environ["CK_MG_INT8_MIN_TILES"] = "48"  # also the tile-column updates and the inverted-tile TRSM of this small case
     try:
         launches0 = lib.ck_launch_count()
         solver = parallel.BlockCyclicCokriging(parallel.ProcessGrid(1, 1), tile=256, lookahead=True)
@@ -66,7 +66,8 @@ def test_block_cyclic_single_rank_int8_updates_vs_oracle():
         pred_d, var_d, _ = parallel.BlockCyclicCokriging(parallel.ProcessGrid(1, 1), tile=256).solve(coords, z, targets, HALF, 2, 1, 0)
         n_dmma = lib.ck_launch_count() - launches0
     finally:
-        lib.ck_oz_configure(1, 4096)
+        lib.ck_oz_configure(1, -1)
+        del os.environ["CK_MG_INT8_MIN_TILES"]
     rp, re, _ = orc.joint_predict(orc.Params(HALF), 1, coords, z, targets, "euclidean")
     assert info == 0 and n_int8 > n_dmma  # the INT8 path launches two splits + one product per big update
     assert np.max(np.abs(pred - rp)) / np.max(np.abs(rp)) < 1e-9
