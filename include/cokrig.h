@@ -277,6 +277,10 @@ int ck_oz_configure(int enabled, ck_i64 min_rows);
 /* 1 if ck_potrf / ck_trsm_lower hand the big updates of an n x n system to the INT8 kernel under the current switches. */
 int ck_oz_active(ck_i64 n);
 
+/* Upper bound on the CTAs (one per SM, persistent) of the following ck_oz_gemm / ck_oz_mg_update launches; 0 = all SMs.
+ * Process-wide, read at enqueue time. */
+int ck_oz_set_grid(int max_ctas);
+
 /* Profiling aid: when set to a device buffer of 8 x 148 int64 counters, every ck_oz_gemm launch stores per-CTA
  * cycle counts there ([0] MMA-issue thread total, [1] waiting for operands, [2] waiting for TMEM, [4] epilogue
  * waiting, [5] epilogue busy).  NULL switches it off (default). */

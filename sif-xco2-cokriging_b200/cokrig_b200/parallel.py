@@ -248,6 +248,13 @@ class CudaKernels:
         m, n, k = A.shape[0], B.shape[0], A.shape[1]
         fa, fb, sa, sb = self._oz_scratch(m, n, k)
         st = o._stream()
+        # optional split of the SMs between the panel stream and the trailing update (CK_MG_PANEL_SMS = R > 0): the
+        # persistent kernel of the main stream leaves R SMs to the look-ahead work of the next tile column
+        r = int(os.environ.get("CK_MG_PANEL_SMS", "0"))
+        if r > 0:
+            nsm = torch.cuda.get_device_properties(self.device).multi_processor_count
+            on_panel = torch.cuda.current_stream(self.device) == self.panel
+            self.lib.ck_oz_set_grid(r if on_panel else max(nsm - r, 1))
         self.check(self.lib.ck_oz_split(o._ptr(A), A.stride(0), m, k, o._ptr(fa), None, o._ptr(sa), st), "ck_oz_split")
         self.check(self.lib.ck_oz_split(o._ptr(B), B.stride(0), n, k, None, o._ptr(fb), o._ptr(sb), st), "ck_oz_split")
         if tb:

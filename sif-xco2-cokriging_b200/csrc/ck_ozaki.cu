@@ -490,6 +490,14 @@ extern "C" int ck_oz_debug_buffer(void* dev_counters) {
   return CK_OK;
 }
 
+// Upper bound on the CTAs (= SMs) of the next ck_oz_gemm / ck_oz_mg_update launches (0 = every SM).  Lets a caller that
+// runs two streams (block-cyclic look-ahead) split the machine between a panel stream and the trailing update.
+static int g_oz_max_ctas = 0;
+extern "C" int ck_oz_set_grid(int max_ctas) {
+  g_oz_max_ctas = max_ctas > 0 ? max_ctas : 0;
+  return CK_OK;
+}
+
 static int oz_num_sms() {
   static int v = 0;
   if (v == 0) {
@@ -531,6 +539,7 @@ static int oz_gemm_launch(const void* a_slices, const double* sa, ck_i64 m, cons
   g.vec = ((((uintptr_t)c) & 15) == 0 && (ldc & 1) == 0) ? 1 : 0;
   g.dbg = g_oz_dbg;
   long long grid = oz_num_sms();
+  if (g_oz_max_ctas > 0 && grid > g_oz_max_ctas) grid = g_oz_max_ctas;
   if (grid > g.nvirt) grid = g.nvirt;
   ck_oz_gemm_kernel<<<(unsigned)grid, OZ_THREADS, OZ_SMEM, ck_stream(stream)>>>(g);
   CK_LAUNCH_CHECK();
