@@ -281,6 +281,10 @@ int ck_oz_active(ck_i64 n);
  * Process-wide, read at enqueue time. */
 int ck_oz_set_grid(int max_ctas);
 
+/* Profiling aid: 16 clock64 stamps (thread 0) of the phases of every following diagonal-block kernel launch
+ * (load, 4 x [32-column elimination, panel, trailing update], inverse assembly, store); NULL = off. */
+int ck_potf2_debug_buffer(void* dev_stamps);
+
 /* Profiling aid: when set to a device buffer of 8 x 148 int64 counters, every ck_oz_gemm launch stores per-CTA
  * cycle counts there ([0] MMA-issue thread total, [1] waiting for operands, [2] waiting for TMEM, [4] epilogue
  * waiting, [5] epilogue busy).  NULL switches it off (default). */

@@ -76,6 +76,7 @@ SIGNATURES = {
                              c_int64, c_int64, c_int64, c_void_p]),
     "ck_row_dots": (c_int, [_dp, c_int64, c_int64, c_int64, _dp, c_int64, _dp, _dp, c_void_p]),
     "ck_oz_configure": (c_int, [c_int, c_int64]),
+    "ck_potf2_debug_buffer": (c_int, [_dp]),
     "ck_oz_active": (c_int, [c_int64]),
     "ck_oz_set_grid": (c_int, [c_int]),
     "ck_oz_debug_buffer": (c_int, [_dp]),

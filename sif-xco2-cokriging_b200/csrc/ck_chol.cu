@@ -293,7 +293,7 @@ static int gemm_launch(const GemmArgs& g, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Diagonal block: L_kk = chol(A_kk) and X_k = L_kk^{-1} (128 x 128), one CTA of 512 threads, the block in
+// Diagonal block: L_kk = chol(A_kk) and X_k = L_kk^{-1} (128 x 128), one CTA of 256 threads, the block in
 // shared memory.  The elimination is blocked in 32-column panels so that the latency-bound part (one
 // dependent pivot per column) runs inside ONE warp with register-resident rows and warp shuffles --
 // no CTA barrier per column -- and everything else is FP64 DMMA on shared-memory operands:
@@ -310,11 +310,12 @@ static int gemm_launch(const GemmArgs& g, cudaStream_t st) {
 constexpr int PB = 32;               // panel width inside the diagonal block
 constexpr int P_LDA = CK_NB + 4;     // smem row stride of the block: % 16 == 4 -> conflict-free DMMA fragment loads
 constexpr int P_LDX = PB + 4;        // row stride of the four diagonal inverse blocks
-constexpr int P_THREADS = 512;
+constexpr int P_THREADS = 256;  // 8 warps: the 32-column elimination keeps 32 + 32 doubles per lane in registers
 constexpr int P_SMEM_DOUBLES = CK_NB * P_LDA + (CK_NB / PB) * PB * P_LDX + CK_NB;
 
 __global__ void __launch_bounds__(P_THREADS, 1)
-    ck_potf2_inv_kernel(double* __restrict__ A, long long ld, int nb, double* __restrict__ X, int* info, int k0) {
+    ck_potf2_inv_kernel(double* __restrict__ A, long long ld, int nb, double* __restrict__ X, int* info, int k0,
+                        long long* __restrict__ dbg) {
   extern __shared__ __align__(16) double sm[];
   double* As = sm;                                   // As[i * P_LDA + k]
   double* Xd = As + CK_NB * P_LDA;                   // Xd[jb][r * P_LDX + c] = (L_d^{-1})[r][c]
@@ -324,13 +325,37 @@ __global__ void __launch_bounds__(P_THREADS, 1)
   const int g4 = lane >> 2, t4 = lane & 3;
   constexpr int NW = P_THREADS / 32;
   if (tid == 0) bad = 0;
-  for (int idx = tid; idx < CK_NB * CK_NB; idx += P_THREADS) {
-    const int i = idx / CK_NB, k = idx % CK_NB;
-    double v = (i == k) ? 1.0 : 0.0;
-    if (i < nb && k < nb) v = (k <= i) ? A[(long long)i * ld + k] : 0.0;
-    As[i * P_LDA + k] = v;
+  int dbg_n = 0;
+#define CK_P_STAMP() do { if (dbg && tid == 0) dbg[dbg_n++] = clock64(); } while (0)
+  CK_P_STAMP();
+  const bool vec = (nb == CK_NB) && ((((uintptr_t)A) & 15) == 0) && ((ld & 1) == 0);
+  if (vec) {
+    // full aligned block: every thread issues its 16 independent 16-byte loads (lower triangle only) before the
+    // first shared-memory store, so one round trip to L2 / HBM covers the whole block
+    constexpr int NV = CK_NB * CK_NB / 2 / P_THREADS;  // double2 per thread
+    double2 v[NV];
+#pragma unroll
+    for (int it = 0; it < NV; ++it) {
+      const int idx = tid + it * P_THREADS, i = idx / (CK_NB / 2), k = 2 * (idx % (CK_NB / 2));
+      v[it] = make_double2(0.0, 0.0);
+      if (k <= i) v[it] = *reinterpret_cast<const double2*>(A + (long long)i * ld + k);
+    }
+#pragma unroll
+    for (int it = 0; it < NV; ++it) {
+      const int idx = tid + it * P_THREADS, i = idx / (CK_NB / 2), k = 2 * (idx % (CK_NB / 2));
+      if (k + 1 > i) v[it].y = 0.0;  // (i, i + 1) is above the diagonal
+      *reinterpret_cast<double2*>(As + i * P_LDA + k) = v[it];
+    }
+  } else {
+    for (int idx = tid; idx < CK_NB * CK_NB; idx += P_THREADS) {
+      const int i = idx / CK_NB, k = idx % CK_NB;
+      double v = (i == k) ? 1.0 : 0.0;
+      if (i < nb && k < nb) v = (k <= i) ? A[(long long)i * ld + k] : 0.0;
+      As[i * P_LDA + k] = v;
+    }
   }
   __syncthreads();
+  CK_P_STAMP();  // 1: block loaded
 
   for (int jb = 0; jb < CK_NB / PB; ++jb) {
     const int c0 = jb * PB;
@@ -341,11 +366,18 @@ __global__ void __launch_bounds__(P_THREADS, 1)
 #pragma unroll
       for (int k = 0; k < PB; ++k) a[k] = As[(c0 + lane) * P_LDA + c0 + k];
       int first_bad = 0;
+      double dk = 1.0;  // pivot of this lane's column
 #pragma unroll
       for (int k = 0; k < PB; ++k) {
         const double d = __shfl_sync(0xffffffffu, a[k], k);
         if (!(d > 0.0) && first_bad == 0) first_bad = c0 + k + 1;
-        const double invd = 1.0 / d;
+        if (lane == k) dk = d;
+        // 1 / d on the critical path: approximate reciprocal + two Newton steps (<= 1 ulp); the square roots are
+        // taken after the loop, for all 32 pivots at once, off the dependency chain
+        double invd;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(invd) : "d"(d));
+        invd = fma(fma(-d, invd, 1.0), invd, invd);
+        invd = fma(fma(-d, invd, 1.0), invd, invd);
         const double u = a[k];
         const double w = u * invd;
 #pragma unroll
@@ -353,15 +385,17 @@ __global__ void __launch_bounds__(P_THREADS, 1)
           const double ujk = __shfl_sync(0xffffffffu, u, j);
           a[j] = fma(-w, ujk, a[j]);
         }
-        const double sq = sqrt(d);
-        const double rs = 1.0 / sq;
-        a[k] = (lane == k) ? sq : u * rs;
-        if (lane == k) rsd[c0 + k] = rs;
       }
+      // a[k] holds the unscaled column entries u_ik (lane = row i); L_ik = u_ik / sqrt(d_k)
+      const double sqv = sqrt(dk);
+      const double rsv = 1.0 / sqv;
+      rsd[c0 + lane] = rsv;
       if (lane == 0 && first_bad != 0 && bad == 0) bad = first_bad;
 #pragma unroll
-      for (int k = 0; k < PB; ++k)
-        if (k <= lane) As[(c0 + lane) * P_LDA + c0 + k] = a[k];
+      for (int k = 0; k < PB; ++k) {
+        const double rs = __shfl_sync(0xffffffffu, rsv, k);
+        if (k <= lane) As[(c0 + lane) * P_LDA + c0 + k] = (lane == k) ? sqv : a[k] * rs;
+      }
       __syncwarp();
       // ---- X_d = L_d^{-1}, lane = column c: forward substitution on e_c; L read by broadcast
       double x[PB];
@@ -377,6 +411,7 @@ __global__ void __launch_bounds__(P_THREADS, 1)
       for (int i = 0; i < PB; ++i) Xdj[i * P_LDX + lane] = x[i];
     }
     __syncthreads();
+    CK_P_STAMP();  // 2 + 3 jb: warp-level elimination + inverse of the 32 x 32 diagonal block
     const int r_begin = c0 + PB;            // first row below the panel
     const int nt = (CK_NB - r_begin) / 8;   // 8-row tiles below
     // ---- panel: P = A[below, c0:c0+32] X_d^T, one 8-row tile (4 output tiles) per warp pass, in place
@@ -401,6 +436,7 @@ __global__ void __launch_bounds__(P_THREADS, 1)
       }
     }
     __syncthreads();
+    CK_P_STAMP();  // 3 + 3 jb: panel
     // ---- trailing: A[below, below] -= P P^T on the lower 8x8 tiles
     const int ntile = nt * (nt + 1) / 2;
     for (int t = warp; t < ntile; t += NW) {
@@ -418,6 +454,7 @@ __global__ void __launch_bounds__(P_THREADS, 1)
       if (!diag || 2 * t4 + 1 <= g4) c[1] = -acc1;
     }
     __syncthreads();
+    CK_P_STAMP();  // 4 + 3 jb: trailing update
   }
 
   // ---- off-diagonal blocks of X = L^{-1}: X_ij = -X_d,i * S_ij, S_ij = sum_{k=j}^{i-1} L_ik X_kj (X_jj = X_d,j).
@@ -443,7 +480,7 @@ __global__ void __launch_bounds__(P_THREADS, 1)
     }
     __syncthreads();
     // stage 2: X_ij = -X_d,i * S_ij (in place: all tiles are computed into registers before any is written)
-    double out[3][2];  // at most 48 tiles over 16 warps
+    double out[(48 + NW - 1) / NW][2];  // at most 48 tiles over NW warps
     int slot = 0;
     for (int t = warp; t < npair * 16; t += NW, ++slot) {
       const int j = t / 16, i = j + dist, mt = (t % 16) / 4, nt_ = t % 4;
@@ -466,17 +503,35 @@ __global__ void __launch_bounds__(P_THREADS, 1)
     __syncthreads();
   }
 
+  CK_P_STAMP();  // 14: inverse assembled
   // ---- results: L in place (lower triangle of the valid part), X dense with an explicit zero upper triangle
-  for (int idx = tid; idx < CK_NB * CK_NB; idx += P_THREADS) {
-    const int i = idx / CK_NB, k = idx % CK_NB;
-    if (i < nb && k <= i) A[(long long)i * ld + k] = As[i * P_LDA + k];
+  // address of X[i][k] (k even addresses a 16-byte aligned pair inside one 32-block): diagonal blocks live in Xd, the
+  // blocks below the diagonal in the (otherwise unused) upper blocks of As; selected without divergence
+  auto xsrc = [&](int i, int k) -> const double* {
     const int bi = i / PB, bj = k / PB, r = i % PB, c = k % PB;
-    double xv = 0.0;
-    if (bi == bj) xv = Xd[bi * PB * P_LDX + r * P_LDX + c];
-    else if (bi > bj) xv = As[(PB * bj + r) * P_LDA + PB * bi + c];
-    X[i * CK_NB + k] = xv;
+    return (bi == bj) ? (Xd + bi * PB * P_LDX + r * P_LDX + c) : (As + (PB * bj + r) * P_LDA + PB * bi + c);
+  };
+  auto xval = [&](int i, int k) { return (i / PB >= k / PB) ? *xsrc(i, k) : 0.0; };
+  if (vec) {
+#pragma unroll 4
+    for (int idx = tid; idx < CK_NB * CK_NB / 2; idx += P_THREADS) {
+      const int i = idx / (CK_NB / 2), k = 2 * (idx % (CK_NB / 2));
+      if (k + 1 <= i) *reinterpret_cast<double2*>(A + (long long)i * ld + k) = *reinterpret_cast<const double2*>(As + i * P_LDA + k);
+      else if (k <= i) A[(long long)i * ld + k] = As[i * P_LDA + k];
+      double2 xv = make_double2(0.0, 0.0);
+      if (i / PB >= k / PB) xv = *reinterpret_cast<const double2*>(xsrc(i, k));
+      *reinterpret_cast<double2*>(X + i * CK_NB + k) = xv;
+    }
+  } else {
+    for (int idx = tid; idx < CK_NB * CK_NB; idx += P_THREADS) {
+      const int i = idx / CK_NB, k = idx % CK_NB;
+      if (i < nb && k <= i) A[(long long)i * ld + k] = As[i * P_LDA + k];
+      X[i * CK_NB + k] = xval(i, k);
+    }
   }
   if (tid == 0 && bad != 0 && *info == 0) *info = k0 + bad;
+  CK_P_STAMP();  // 15: stored (this thread's part)
+#undef CK_P_STAMP
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -604,6 +659,13 @@ extern "C" size_t ck_potrf_workspace_bytes(ck_i64 n) {
   return b;
 }
 
+// profiling aid (tools): 16 clock64 stamps of the last diagonal-block kernel launched
+static long long* g_potf2_dbg = nullptr;
+extern "C" int ck_potf2_debug_buffer(void* dev_stamps) {
+  g_potf2_dbg = static_cast<long long*>(dev_stamps);
+  return CK_OK;
+}
+
 static int potf2_launch(double* a, long long ld, int nb, double* x, int* info, int k0, cudaStream_t st) {
   constexpr size_t SMEM = P_SMEM_DOUBLES * sizeof(double);
   static bool attr_done = false;
@@ -611,7 +673,7 @@ static int potf2_launch(double* a, long long ld, int nb, double* x, int* info, i
     CK_CUDA(cudaFuncSetAttribute(ck_potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     attr_done = true;
   }
-  ck_potf2_inv_kernel<<<1, P_THREADS, SMEM, st>>>(a, ld, nb, x, info, k0);
+  ck_potf2_inv_kernel<<<1, P_THREADS, SMEM, st>>>(a, ld, nb, x, info, k0, g_potf2_dbg);
   CK_LAUNCH_CHECK();
   return CK_OK;
 }
