@@ -269,7 +269,7 @@ int ck_row_dots(const double* v_dev, ck_i64 ldv, ck_i64 nrows, ck_i64 ncols, con
  * ---------------------------------------------------------------------------------------------- */
 
 /* Process-wide switches of the INT8 path (negative value = leave unchanged): enabled (default 1, env CK_OZAKI)
- * and the smallest trailing dimension handed to it (default 4096, env CK_OZ_MIN_ROWS; matrices smaller than
+ * and the smallest trailing dimension handed to it (default 1024, env CK_OZ_MIN_ROWS; matrices smaller than
  * twice that, or than 2048, are factored by the FP64 DMMA kernel alone).  The workspace size does not depend on
  * these switches. */
 int ck_oz_configure(int enabled, ck_i64 min_rows);

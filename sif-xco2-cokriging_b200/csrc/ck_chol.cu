@@ -614,7 +614,7 @@ static int oz_enabled() {
 static ck_i64 oz_min_rows() {
   if (g_oz_min_rows < 0) {
     const char* e = getenv("CK_OZ_MIN_ROWS");
-    g_oz_min_rows = e ? atoll(e) : 4096;
+    g_oz_min_rows = e ? atoll(e) : 1024;
     if (g_oz_min_rows < 128) g_oz_min_rows = 128;
   }
   return g_oz_min_rows;

@@ -28,7 +28,7 @@ def int8_path_small(lib):
     """Hand even small trailing matrices to the INT8 kernel; restore the defaults afterwards."""
     lib.lib.ck_oz_configure(1, 256)
     yield
-    lib.lib.ck_oz_configure(1, 4096)
+    lib.lib.ck_oz_configure(1, 1024)
 
 
 def _stream():
