@@ -327,9 +327,10 @@ def run_gpu(args, n_per_var: int, m: int) -> None:
                                     "frac_of_2x_bf16_burst": int8_ops_launch / launch_ms / 1e9 / (2 * bf16_burst),
                                     "fp64_equiv_TFs": int8_ops_launch / 28 / launch_ms / 1e9},
                 "fp64_equiv_TFs": achieved_tf, "dgemm_live_TFs": dgemm_tf, "fp64_equiv_over_dgemm": achieved_tf / dgemm_tf,
-                # ncu --set full of one launch (profiles/r01i_ozgemm_ncu_full_summary.txt: 32768 x 32768 lower, K = 1024):
-                # dram read 17.27 GB + write 4.27 GB; algorithmic 8.59 GB of C + 0.47 GB of slices
-                "traffic": 21.54e9, "traffic_note": "per launch at rows=32768 (ncu), algorithmic 9.06e9",
+                # ncu --set full of this launch shape (profiles/r01z_ozgemm_ncu_full_summary.txt: rows = 38976, lower, K = 1024):
+                # dram read 30.27 GB + write 6.07 GB; algorithmic 12.15 GB of C (read + write) + 0.56 GB of slices
+                "traffic": 36.34e9, "traffic_note": "per launch at rows=38976 (ncu r01z), algorithmic 12.7e9: the operand "
+                                                    "slices are re-read ~20x from DRAM (L2 hit rate 70 %)",
                 "flops_per_step": fp64_flops}
         else:
             roofline = {"bound": "tensor", "kernel": "ck_gemm_nt_kernel (FP64 DMMA: DSYRK trailing + TRSM updates)",

@@ -273,8 +273,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ck_oz_gemm_kernel(OzGemmArgs g)
   extern __shared__ uint8_t oz_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)oz_smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)OZ_NSTAGE * OZ_STAGE);
-  // bars[0..3] full, [4..7] empty, [8] tmem_full, [9] tmem_empty, then the TMEM base address
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  // bars[0..S) full, [S..2S) empty, [2S] tmem_full, [2S+1] tmem_empty (S = OZ_NSTAGE), then the TMEM base address
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * OZ_NSTAGE + 2);
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (OZ_NSTAGE + s); };
