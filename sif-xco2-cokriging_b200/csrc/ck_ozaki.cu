@@ -223,6 +223,7 @@ struct OzGemmArgs {
   int ni, nj;         // 128-row blocks of A, 64-row blocks of B
   int lower;          // 1: only entries with col <= row are updated (tiles above the diagonal are skipped)
   int tri;            // 1: triangular virtual tile space (square lower update), 0: rectangular
+  int sr;             // row blocks per super-row of the tile order
   long long nvirt;    // virtual tiles
   // block-cyclic mode (tb > 0): C is the local part of a 2-D block-cyclic matrix with square tiles of tb elements; local
   // tile (li, lj) is global tile (gi0 + li gis, gj0 + lj gjs); tiles with J > I are skipped, tiles with J == I keep
@@ -233,22 +234,25 @@ struct OzGemmArgs {
   long long* dbg;     // optional per-CTA cycle counters (8 per CTA), see ck_oz_debug_buffer
 };
 
-// virtual tile t -> (I, j).  Tiles are ordered in super-rows of 8 row blocks, inside a super-row column-major
-// (j outer, I inner), so that the ~148 tiles in flight share 8 A blocks and ~18 B blocks (L2 reuse).
+// virtual tile t -> (I, j).  Tiles are ordered in super-rows of sr (default 16, CK_OZ_SUPER_ROWS) row blocks, inside a
+// super-row column-major (j outer, I inner), so that the ~148 tiles in flight share 16 A blocks and ~9 B blocks (L2 reuse).
 __device__ __forceinline__ bool oz_decode(const OzGemmArgs& g, long long t, int& I, int& j) {
   long long s, u;
+  const long long sr = g.sr;  // row blocks per super-row
   if (g.tri) {
-    s = (long long)((sqrt(1.0 + (double)t * (1.0 / 16.0)) - 1.0) * 0.5);
-    while (64 * (s + 1) * (s + 2) <= t) ++s;
-    while (64 * s * (s + 1) > t) --s;
-    u = t - 64 * s * (s + 1);
+    // super-row s holds sr row blocks x 2 sr (s + 1) column blocks; prefix sum sr^2 s (s + 1)
+    const long long q = sr * sr;
+    s = (long long)((sqrt(1.0 + 4.0 * (double)t / (double)q) - 1.0) * 0.5);
+    while (q * (s + 1) * (s + 2) <= t) ++s;
+    while (q * s * (s + 1) > t) --s;
+    u = t - q * s * (s + 1);
   } else {
-    const long long w = 8LL * g.nj;
+    const long long w = sr * g.nj;
     s = t / w;
     u = t - s * w;
   }
-  j = (int)(u >> 3);
-  I = (int)(8 * s + (u & 7));
+  j = (int)(u / sr);
+  I = (int)(sr * s + (u % sr));
   if (I >= g.ni || j >= g.nj) return false;
   if (g.tb) {
     const long long li = ((long long)I * OZ_TM) / g.tb, lj = ((long long)j * OZ_TN) / g.tb;
@@ -531,11 +535,18 @@ static int oz_gemm_launch(const void* a_slices, const double* sa, ck_i64 m, cons
   g.nj = (int)((n + OZ_TN - 1) / OZ_TN);
   g.lower = (lower && !tb) ? 1 : 0;
   g.tb = (int)tb; g.gi0 = gi0; g.gis = gis; g.gj0 = gj0; g.gjs = gjs;
-  const long long srows = (g.ni + 7) / 8;
+  static int sr_cfg = 0;
+  if (sr_cfg == 0) {
+    const char* e = getenv("CK_OZ_SUPER_ROWS");
+    sr_cfg = e ? atoi(e) : 16;  // measured on the largest C3 update: 8 -> 94, 16 -> 97, 32 -> 98 TFLOP/s; DRAM reads 30 -> 22 GB
+    if (sr_cfg < 1 || sr_cfg > 64) sr_cfg = 16;
+  }
+  g.sr = sr_cfg;
+  const long long srows = (g.ni + g.sr - 1) / g.sr;
   // the triangular tile space needs every super-row s to hold its 16 s + 16 column blocks; use it for (near-)square
   // lower updates, the rectangular space otherwise
   g.tri = (g.lower && (long long)g.nj >= 2LL * g.ni - 1) ? 1 : 0;
-  g.nvirt = g.tri ? 64 * srows * (srows + 1) : srows * 8LL * g.nj;
+  g.nvirt = g.tri ? (long long)g.sr * g.sr * srows * (srows + 1) : srows * (long long)g.sr * g.nj;
   g.vec = ((((uintptr_t)c) & 15) == 0 && (ldc & 1) == 0) ? 1 : 0;
   g.dbg = g_oz_dbg;
   long long grid = oz_num_sms();
