@@ -229,7 +229,7 @@ def gaussian_nll(coords: Sequence[torch.Tensor], z: torch.Tensor, params, n_proc
 
 
 # ------------------------------------------------------------------------------------------------ K2
-VARIO_GUARD = 1.8e-15  # must match CK_VARIO_GUARD (csrc/ck_vario.cu)
+VARIO_GUARD = 2.0e-14  # must match CK_VARIO_GUARD (csrc/ck_vario.cu)
 VARIO_LIST_CAPACITY = 1 << 16
 
 

@@ -40,6 +40,17 @@ static inline int vario_warps(int n_bins) {
 
 __device__ __forceinline__ unsigned long long dbits(double d) { return (unsigned long long)__double_as_longlong(d); }
 
+// Pair distance of the binning kernels.  Euclidean: the reference-order function (bit-identical to scipy cdist, so bin
+// decisions need no guard).  Haversine: the branch-free polynomial path of the assembly kernel (ck_math.cuh), <= 4e-15
+// relative from the host's libm evaluation for pairs more than ~1000 km from the antipode; every decision inside the
+// guard band CK_VARIO_GUARD (5x that) is left to the host, which re-evaluates those pairs with libm.  (Within ~100 km of the
+// antipode asin(sqrt(a)) amplifies the last-bit rounding of a beyond any fixed relative band -- for the device AND for
+// libm; variogram ranges never reach there: pairs beyond max_dist (1 + guard) are dropped before any decision.)
+template <int METRIC>
+__device__ __forceinline__ double vario_dist(const CkPoint& p, const CkPoint& q) {
+  return METRIC == CK_METRIC_HAVERSINE ? ck_dist_haversine_fast(p, q) : ck_dist_euclid(p, q);
+}
+
 // ------------------------------------------------------------------------------------------------
 // pass 1: min non-zero distance, max distance and number of pairs with d <= max_dist
 // (min / max are order-free, so plain atomics on the bit patterns of non-negative doubles are exact)
@@ -72,7 +83,7 @@ __global__ void __launch_bounds__(256) ck_vario_minmax_kernel(const double* __re
       const int ib = lane + 32 * q;
       const long long gb = b0 + ib;
       if (gb < nb && (!same_field || gb > ga)) {
-        const double d = ck_dist<METRIC>(p, pb[ib]);
+        const double d = vario_dist<METRIC>(p, pb[ib]);
         if (d <= max_dist) {  // max_dist already widened by the guard band for inexact metrics
           const unsigned long long u = dbits(d);
           ++cnt;
@@ -138,7 +149,7 @@ __global__ void __launch_bounds__(256) ck_vario_candidates_kernel(const double* 
       const int ib = lane + 32 * q;
       const long long gb = b0 + ib;
       if (gb < nb && (!same_field || gb > ga)) {
-        const double d = ck_dist<METRIC>(p, pb[ib]);
+        const double d = vario_dist<METRIC>(p, pb[ib]);
         if (d <= dlim && ((d > 0.0 && d <= lo) || d >= hi)) {
           const unsigned long long pos = atomicAdd(count, 1ULL);
           if ((long long)pos < capacity) { pairs[2 * pos] = ga; pairs[2 * pos + 1] = gb; }
@@ -160,9 +171,9 @@ __global__ void ck_vario_minmax_final_kernel(unsigned long long* out) {
   o[2] = (double)cnt;
 }
 
-// relative half-width of the guard band around decision boundaries (~8 ulp); haversine only --
-// Euclidean distances are bit-identical to scipy's and need no guard
-#define CK_VARIO_GUARD 1.8e-15
+// relative half-width of the guard band around decision boundaries (~90 ulp, 5x the measured device-vs-libm deviation of
+// the fast haversine); haversine only -- Euclidean distances are bit-identical to scipy's and need no guard
+#define CK_VARIO_GUARD 2.0e-14
 static inline double vario_dlim(int metric, double max_dist) {
   return metric == CK_METRIC_HAVERSINE ? max_dist * (1.0 + CK_VARIO_GUARD) : max_dist;
 }
@@ -296,7 +307,7 @@ __global__ void __launch_bounds__(256) ck_vario_bin_kernel(VarioBinArgs g, int n
       const int ib = lane + 32 * q;
       const long long gb = b0 + ib;
       if (gb < g.nb && (!g.same_field || gb > ga)) {
-        const double d = ck_dist<METRIC>(p, pb[ib]);
+        const double d = vario_dist<METRIC>(p, pb[ib]);
         if (d <= g.dlim && d >= e_first) {
           int k = (int)((d - g.e1) * g.inv_w) + 1;
           k = k < 0 ? 0 : (k > nb_ - 1 ? nb_ - 1 : k);
