@@ -624,6 +624,28 @@ extern "C" int ck_oz_configure(int enabled, ck_i64 min_rows) {
   if (min_rows >= 0) g_oz_min_rows = min_rows < 128 ? 128 : min_rows;
   return CK_OK;
 }
+// Look-ahead beside the persistent INT8 kernel: the update of aggregate j is split into (a) the columns of aggregate
+// j + 1 (all SMs) and (b) the rest, launched on all but CK_OZ_LA_SMS SMs, while the panel chain of aggregate j + 1 (FP64
+// DMMA + one-CTA diagonal blocks, mostly latency-bound) runs on a high-priority side stream on the SMs left free.
+// Used while (b) is long enough to hide the chain (trailing dimension >= CK_OZ_LA_MIN_ROWS).  CK_OZ_LA_SMS=0: off.
+static int oz_la_sms() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CK_OZ_LA_SMS");
+    v = e ? atoi(e) : 10;
+    if (v < 0 || v > 100) v = 10;
+  }
+  return v;
+}
+static ck_i64 oz_la_min_rows() {
+  static ck_i64 v = -1;
+  if (v < 0) {
+    const char* e = getenv("CK_OZ_LA_MIN_ROWS");
+    v = e ? atoll(e) : 8192;
+    if (v < 1024) v = 1024;
+  }
+  return v;
+}
 constexpr ck_i64 OZ_KMAX = 1024;  // deepest update one split covers (ck_oz_split)
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 static size_t xinv_bytes(ck_i64 n) {
@@ -804,22 +826,55 @@ extern "C" int ck_potrf(double* a, ck_i64 n, ck_i64 ld, void* ws, int* info, voi
     // Big trailing updates on the INT8 tensor cores: per aggregate, the panel chain (FP64 DMMA, recursive), one split
     // of the finished panel into digit slices, one persistent tcgen05 kernel over the lower tiles of the trailing matrix.
     const OzScratch z = oz_scratch(ws, n);
+    const int la = oz_la_sms();
+    SideStream* oside = nullptr;
+    if (la > 0 && lookahead_enabled() && n >= 2 * oz_la_min_rows()) {
+      if ((rc = side_stream(st, &oside))) return rc;
+    }
+    std::unique_lock<std::mutex> oturn;
+    if (oside) oturn = std::unique_lock<std::mutex>(oside->enqueue);
+    CholCtx ocs = c;
+    if (oside) ocs.st = oside->s;
+    if ((rc = factor_range(c, 0, agg < nblk ? agg : nblk))) return rc;
     for (ck_i64 b0 = 0; b0 < nblk; b0 += agg) {
       const ck_i64 b1 = b0 + agg < nblk ? b0 + agg : nblk;
-      if ((rc = factor_range(c, b0, b1))) return rc;
       const ck_i64 k0 = c.s(b0), k1 = c.s(b1);
       if (k1 >= n) break;
-      const ck_i64 rows = n - k1, kk = k1 - k0;
-      if (rows >= oz_min_rows() && kk % 32 == 0) {
+      const ck_i64 b2 = b1 + agg < nblk ? b1 + agg : nblk;
+      const ck_i64 k2 = c.s(b2);
+      const ck_i64 rows = n - k1, kk = k1 - k0, off = k2 - k1;
+      const bool use_oz = rows >= oz_min_rows() && kk % 32 == 0;
+      const bool la_now = oside && use_oz && (n - k2) >= oz_la_min_rows() && off % 128 == 0;
+      if (use_oz) {
         if ((rc = ck_oz_split(a + k1 * ld + k0, ld, rows, kk, z.fa, z.fb, z.sa, stream))) return rc;
-        if ((rc = ck_oz_gemm(z.fa, z.sa, rows, z.fb, z.sa, rows, kk, a + k1 * ld + k1, ld, 1, stream))) return rc;
+      }
+      if (la_now) {
+        // (a) columns of the next aggregate: A[k1:, k1:k2] -= P P[k1:k2]^T  (every SM)
+        if ((rc = ck_oz_gemm(z.fa, z.sa, rows, z.fb, z.sa, off, kk, a + k1 * ld + k1, ld, 1, stream))) return rc;
+        CK_CUDA(cudaEventRecord(oside->ev_a, st));
+        CK_CUDA(cudaStreamWaitEvent(oside->s, oside->ev_a, 0));
+        if ((rc = factor_range(ocs, b1, b2))) return rc;  // panel chain of the next aggregate, beside (b)
+        CK_CUDA(cudaEventRecord(oside->ev_c, oside->s));
+        // (b) the rest: A[k2:, k2:] -= P[k2:] P[k2:]^T on all but `la` SMs
+        const char* fa2 = static_cast<const char*>(z.fa) + (size_t)(off / 128) * ck_oz_slices_bytes(128, kk, 0);
+        const char* fb2 = static_cast<const char*>(z.fb) + (size_t)(off / 64) * ck_oz_slices_bytes(64, kk, 1);
+        const int old_cap = ck_oz_grid_swap(ck_oz_num_sms() - la);
+        rc = ck_oz_gemm(fa2, z.sa + off, rows - off, fb2, z.sa + off, rows - off, kk, a + k2 * ld + k2, ld, 1, stream);
+        ck_oz_grid_swap(old_cap);
+        if (rc) return rc;
+        CK_CUDA(cudaStreamWaitEvent(st, oside->ev_c, 0));
       } else {
-        GemmArgs u;  // A[k1:, k1:] -= P P^T, P = A[k1:, k0:k1], lower tiles
-        u.A = a + k1 * ld + k0; u.lda = ld;
-        u.B = a + k1 * ld + k0; u.ldb = ld;
-        u.C = a + k1 * ld + k1; u.ldc = ld;
-        u.M = rows; u.N = rows; u.K = kk; u.mode = 1; u.lower_only = 1;
-        if ((rc = gemm_launch<4, 2>(u, st))) return rc;
+        if (use_oz) {
+          if ((rc = ck_oz_gemm(z.fa, z.sa, rows, z.fb, z.sa, rows, kk, a + k1 * ld + k1, ld, 1, stream))) return rc;
+        } else {
+          GemmArgs u;  // A[k1:, k1:] -= P P^T, P = A[k1:, k0:k1], lower tiles
+          u.A = a + k1 * ld + k0; u.lda = ld;
+          u.B = a + k1 * ld + k0; u.ldb = ld;
+          u.C = a + k1 * ld + k1; u.ldc = ld;
+          u.M = rows; u.N = rows; u.K = kk; u.mode = 1; u.lower_only = 1;
+          if ((rc = gemm_launch<4, 2>(u, st))) return rc;
+        }
+        if ((rc = factor_range(c, b1, b2))) return rc;
       }
     }
     return CK_OK;
@@ -915,23 +970,55 @@ extern "C" int ck_trsm_lower(const double* l, ck_i64 n, ck_i64 ld, const void* w
     // INT8 tensor-core updates (see ck_potrf).  The slice scratch lives behind the block inverses in the
     // factorisation workspace: solves that share one factor must not run concurrently.
     const OzScratch z = oz_scratch(const_cast<void*>(ws), n);
+    const int la = oz_la_sms();
+    SideStream* oside = nullptr;
+    if (la > 0 && lookahead_enabled() && n >= 2 * oz_la_min_rows()) {
+      if ((rc = side_stream(st, &oside))) return rc;
+    }
+    std::unique_lock<std::mutex> oturn;
+    if (oside) oturn = std::unique_lock<std::mutex>(oside->enqueue);
+    TrsmCtx ocs = c;
+    if (oside) ocs.st = oside->s;
+    if ((rc = solve_range(c, 0, agg < nblk ? agg : nblk))) return rc;
     for (ck_i64 b0 = 0; b0 < nblk; b0 += agg) {
       const ck_i64 b1 = b0 + agg < nblk ? b0 + agg : nblk;
-      if ((rc = solve_range(c, b0, b1))) return rc;
       const ck_i64 k0 = c.s(b0), k1 = c.s(b1);
       if (k1 >= n) break;
-      const ck_i64 cols = n - k1, kk = k1 - k0;
-      if (cols >= oz_min_rows() && kk % 32 == 0) {
+      const ck_i64 b2 = b1 + agg < nblk ? b1 + agg : nblk;
+      const ck_i64 k2 = c.s(b2);
+      const ck_i64 cols = n - k1, kk = k1 - k0, off = k2 - k1;
+      const bool use_oz = cols >= oz_min_rows() && kk % 32 == 0;
+      const bool la_now = oside && use_oz && (n - k2) >= oz_la_min_rows() && off % 64 == 0;
+      if (use_oz) {
         if ((rc = ck_oz_split(rhs + k0, ld_rhs, nrhs, kk, z.fa, nullptr, z.sa, stream))) return rc;
         if ((rc = ck_oz_split(l + k1 * ld + k0, ld, cols, kk, nullptr, z.fb, z.sb, stream))) return rc;
-        if ((rc = ck_oz_gemm(z.fa, z.sa, nrhs, z.fb, z.sb, cols, kk, rhs + k1, ld_rhs, 0, stream))) return rc;
+      }
+      if (la_now) {
+        // (a) columns of the next aggregate: R[:, k1:k2] -= V L[k1:k2]^T  (every SM)
+        if ((rc = ck_oz_gemm(z.fa, z.sa, nrhs, z.fb, z.sb, off, kk, rhs + k1, ld_rhs, 0, stream))) return rc;
+        CK_CUDA(cudaEventRecord(oside->ev_a, st));
+        CK_CUDA(cudaStreamWaitEvent(oside->s, oside->ev_a, 0));
+        if ((rc = solve_range(ocs, b1, b2))) return rc;  // small solves of the next aggregate, beside (b)
+        CK_CUDA(cudaEventRecord(oside->ev_c, oside->s));
+        // (b) the rest: R[:, k2:] -= V L[k2:]^T on all but `la` SMs
+        const char* fb2 = static_cast<const char*>(z.fb) + (size_t)(off / 64) * ck_oz_slices_bytes(64, kk, 1);
+        const int old_cap = ck_oz_grid_swap(ck_oz_num_sms() - la);
+        rc = ck_oz_gemm(z.fa, z.sa, nrhs, fb2, z.sb + off, cols - off, kk, rhs + k2, ld_rhs, 0, stream);
+        ck_oz_grid_swap(old_cap);
+        if (rc) return rc;
+        CK_CUDA(cudaStreamWaitEvent(st, oside->ev_c, 0));
       } else {
-        GemmArgs r;  // R[:, k1:] -= V[:, k0:k1] L[k1:, k0:k1]^T
-        r.A = rhs + k0; r.lda = ld_rhs;
-        r.B = l + k1 * ld + k0; r.ldb = ld;
-        r.C = rhs + k1; r.ldc = ld_rhs;
-        r.M = nrhs; r.N = cols; r.K = kk; r.mode = 1; r.lower_only = 0;
-        if ((rc = gemm_launch<4, 2>(r, st))) return rc;
+        if (use_oz) {
+          if ((rc = ck_oz_gemm(z.fa, z.sa, nrhs, z.fb, z.sb, cols, kk, rhs + k1, ld_rhs, 0, stream))) return rc;
+        } else {
+          GemmArgs r;  // R[:, k1:] -= V[:, k0:k1] L[k1:, k0:k1]^T
+          r.A = rhs + k0; r.lda = ld_rhs;
+          r.B = l + k1 * ld + k0; r.ldb = ld;
+          r.C = rhs + k1; r.ldc = ld_rhs;
+          r.M = nrhs; r.N = cols; r.K = kk; r.mode = 1; r.lower_only = 0;
+          if ((rc = gemm_launch<4, 2>(r, st))) return rc;
+        }
+        if ((rc = solve_range(c, b1, b2))) return rc;
       }
     }
     return CK_OK;

@@ -54,4 +54,8 @@ int ck_block_matern(const CkParams& p, int i, int j, int use_nugget, CkMatern* o
 int ck_block_launch(const double* xy1, ck_i64 n1, const double* xy2, ck_i64 n2, int metric, const CkMatern& P, int value,
                     double* out, ck_i64 ld, double* out_t, ck_i64 ld_t, int symmetric, cudaStream_t st);
 
+// INT8 update kernel (ck_ozaki.cu): CTA cap of the following launches (returns the previous cap; 0 = every SM), SM count
+int ck_oz_grid_swap(int max_ctas);
+int ck_oz_num_sms();
+
 static inline cudaStream_t ck_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }

@@ -502,6 +502,12 @@ extern "C" int ck_oz_set_grid(int max_ctas) {
   return CK_OK;
 }
 
+int ck_oz_grid_swap(int max_ctas) {  // internal (ck_common.cuh): set the cap, return the previous one
+  const int old = g_oz_max_ctas;
+  g_oz_max_ctas = max_ctas > 0 ? max_ctas : 0;
+  return old;
+}
+
 static int oz_num_sms() {
   static int v = 0;
   if (v == 0) {
@@ -511,6 +517,7 @@ static int oz_num_sms() {
   }
   return v;
 }
+int ck_oz_num_sms() { return oz_num_sms(); }
 
 static int oz_gemm_launch(const void* a_slices, const double* sa, ck_i64 m, const void* b_slices, const double* sb, ck_i64 n,
                           ck_i64 k, double* c, ck_i64 ldc, int lower, ck_i64 tb, ck_i64 gi0, ck_i64 gis, ck_i64 gj0, ck_i64 gjs,
