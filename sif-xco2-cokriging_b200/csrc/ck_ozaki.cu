@@ -25,8 +25,8 @@
 //                      in shared memory with the row-group stride of one slice, so A_p x [B_q..B_q+3] is ONE
 //                      M=128, N=256 instruction whose 256 accumulator columns are exactly the group blocks
 //                      p+q..p+q+3 (A is read 10 times per chunk instead of 28).
-//   warps 2-9 epilogue: tcgen05.ld the 7 int32 group blocks, Horner in FP64 (v = v 2^-8 + G_g, exact
-//                      conversions), scale by s_a s_b (powers of two: exact) and C -= v.
+//   warps 2-9 epilogue: tcgen05.ld the 7 int32 group blocks, exact 64-bit integer recombination three groups at a
+//                      time, 3 conversions + 2 FMAs in FP64, scale by s_a s_b (powers of two: exact) and C -= v.
 #include <stdint.h>
 #include <stdlib.h>
 #include "ck_common.cuh"
@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ck_oz_gemm_kernel(OzGemmArgs g)
       const long long row = (long long)I * OZ_TM + 32 * qd + lane;
       const long long cb = (long long)j * OZ_TN + EC * half;
       const bool row_ok = row < g.m;
-      const double srow = row_ok ? g.sa[row] : 0.0;
+      const double srow = row_ok ? g.sa[row] * 1.52587890625e-05 /* 2^-16, see the recombination below */ : 0.0;
       double* crow = g.c + (row_ok ? row : 0) * g.ldc + cb;
       const double sb_l = (cb + lane < g.n) ? __ldg(g.sb + cb + lane) : 0.0;
       const long long clim = oz_col_limit(g, row_ok ? row : 0, j);
@@ -425,12 +425,17 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ck_oz_gemm_kernel(OzGemmArgs g)
         tc_wait_ld();
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          double h = (double)acc[OZ_S - 1][i];
-#pragma unroll
-          for (int gb = OZ_S - 2; gb >= 0; --gb) h = fma(h, 0.00390625, (double)acc[gb][i]);
+          // sum_g 2^(-8g) G_g: the groups are combined three at a time in exact 64-bit integer arithmetic
+          // (|G_g| < 2^28, so |G_0 2^16 + G_1 2^8 + G_2| < 2^45), which leaves 3 conversions + 2 FMAs on the FP64 pipe
+          // instead of 7 + 6 -- the drain of the accumulators is FP64-pipe bound
+          static_assert(OZ_S == 7, "group recombination is written for 7 slices");
+          const long long t0 = ((long long)acc[0][i] << 16) + ((long long)acc[1][i] << 8) + (long long)acc[2][i];
+          const long long t1 = ((long long)acc[3][i] << 16) + ((long long)acc[4][i] << 8) + (long long)acc[5][i];
+          double h = fma((double)t1, 5.9604644775390625e-08 /* 2^-24 */, (double)t0);
+          h = fma((double)acc[6][i], 2.3283064365386963e-10 /* 2^-32 */, h);
           const int cl = 8 * c8 + i;
           const double sbv = __shfl_sync(0xffffffffu, sb_l, cl);
-          creg[cl] -= h * (srow * sbv);
+          creg[cl] -= h * (srow * sbv);  // srow carries the remaining 2^-16
         }
       }
       tc_fence_before();

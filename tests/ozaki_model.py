@@ -2,7 +2,8 @@
 
 Same arithmetic as the kernels: per-row power-of-two scaling to (0.49, 0.98], ONE rounding to a 55-bit fixed-point
 integer, exact recoding into 7 balanced base-256 digits, exact integer slice products G_g = sum_{p+q=g} A_p B_q^T
-for g = 0..6 (int32 range checked), FP64 Horner recombination v = v / 256 + G_g, exact power-of-two scaling."""
+for g = 0..6 (int32 range checked), exact integer recombination three groups at a time + two FP64 fused multiply-adds,
+exact power-of-two scaling."""
 import numpy as np
 
 S = 7
@@ -30,12 +31,17 @@ def product(a: np.ndarray, b: np.ndarray) -> np.ndarray:
     assert a.shape[1] == b.shape[1] <= 1024
     da, sa = split(a)
     db, sb = split(b)
-    v = None
-    for g in range(S - 1, -1, -1):
-        G = sum(da[p] @ db[g - p].T for p in range(g + 1))  # exact: |G| < 2^31 << 2^53
-        assert np.abs(G).max() < 2 ** 31
-        v = G if v is None else v * 0.00390625 + G
-    return v * sa[:, None] * sb[None, :]
+    G = []
+    for g in range(S):
+        G.append(sum(da[p] @ db[g - p].T for p in range(g + 1)))  # exact: |G| < 2^31 << 2^53
+        assert np.abs(G[-1]).max() < 2 ** 31
+    # recombination as in the kernel epilogue: three groups at a time in exact integer arithmetic (|t| < 2^45),
+    # then two fused multiply-adds (the scalings by powers of two are exact, each addition rounds once)
+    t0 = G[0] * 65536.0 + G[1] * 256.0 + G[2]
+    t1 = G[3] * 65536.0 + G[4] * 256.0 + G[5]
+    v = t1 * 2.0 ** -24 + t0
+    v = G[6] * 2.0 ** -32 + v
+    return v * 2.0 ** -16 * sa[:, None] * sb[None, :]
 
 
 def cholesky_blocked(sigma: np.ndarray, nb: int, gemm) -> np.ndarray:
