@@ -179,3 +179,38 @@ def test_joint_prediction_with_int8_updates_vs_oracle(lib, int8_path_small):
     assert factor.info == 0
     assert np.max(np.abs(pred.cpu().numpy() - ref_pred)) / np.abs(ref_pred).max() < 1e-9
     assert np.max(np.abs(var.cpu().numpy() - ref_err ** 2)) < 1e-9 * 1.01
+
+
+def test_factor_and_solve_at_scale_with_lookahead(lib):
+    """N = 18 000, 1 100 right-hand sides: large enough for the look-ahead beside the persistent INT8 kernel (panel chain
+    of the next aggregate on a side stream).  Size-independent checks -- sampled rows of L L^T against Sigma, solve
+    residuals, bit-reproducibility -- and agreement with the FP64 DMMA path on the same inputs."""
+    import torch
+    from cokrig_b200 import METRIC_EUCLID, ops
+    n = 9000
+    xy = ops.coords_to_device(np.random.default_rng(4).uniform(0, 1, (n, 2)))
+    params = [1, .8, 1.5, 1.5, 1.5, .05, .05, .05, .02, .02, -.2]
+    S0 = ops.joint_cov([xy, xy], params, 2, METRIC_EUCLID)
+    f = ops.potrf(S0.clone())
+    assert f.info == 0
+    L = f.lower()
+    idx = torch.randint(0, 2 * n, (100,), device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    assert ((L[idx] @ L.T) - S0[idx]).abs().max().item() < 1e-11
+    m = 1100
+    B = torch.randn((m, 2 * n), dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(2))
+    rb = torch.empty((m, ops.padded_ld(2 * n)), dtype=torch.float64, device="cuda")[:, : 2 * n]
+    rb.copy_(B)
+    V = f.solve_lower(rb)
+    assert ((V[:50] @ L.T) - B[:50]).abs().max().item() < 1e-9
+    f2 = ops.potrf(S0.clone())
+    assert torch.equal(torch.tril(f2.L), L), "factorisation must be bit-reproducible (look-ahead included)"
+    lib.lib.ck_oz_configure(0, -1)
+    try:
+        fd = ops.potrf(S0.clone())
+        rb2 = torch.empty((m, ops.padded_ld(2 * n)), dtype=torch.float64, device="cuda")[:, : 2 * n]
+        rb2.copy_(B)
+        Vd = fd.solve_lower(rb2)
+    finally:
+        lib.lib.ck_oz_configure(1, -1)
+    assert (fd.lower() - L).abs().max().item() / L.abs().max().item() < 1e-13
+    assert (Vd - V).abs().max().item() / V.abs().max().item() < 1e-11
