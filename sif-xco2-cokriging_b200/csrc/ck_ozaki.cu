@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(256) ck_oz_split_kernel(const double* __restri
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
   int ex = 0;
-  if (amax > 0.0 && amax < 1.0e300) {
+  if (amax > 0.0 && amax <= 1.7976931348623157e308) {
     const double f = frexp(amax, &ex);  // amax = f 2^ex, f in [0.5, 1)
     if (f > 0.98) ++ex;                 // |a| 2^-ex <= 0.98: the leading digit stays inside [-126, 126]
     if (ex < -900) ex = -900;
@@ -514,7 +514,7 @@ int ck_oz_grid_swap(int max_ctas) {  // internal (ck_common.cuh): set the cap, r
 }
 
 static int oz_num_sms() {
-  static int v = 0;
+  static int v = 0;  // one process drives identical GPUs
   if (v == 0) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 148;
@@ -533,10 +533,14 @@ static int oz_gemm_launch(const void* a_slices, const double* sa, ck_i64 m, cons
   CK_REQUIRE(k % OZ_KC == 0 && k <= 1024, "k (%lld) must be a multiple of 32 and <= 1024", (long long)k);
   CK_REQUIRE(ldc >= n, "ldc (%lld) < n (%lld)", (long long)ldc, (long long)n);
   CK_REQUIRE((((uintptr_t)a_slices | (uintptr_t)b_slices) & 15) == 0, "slice buffers must be 16-byte aligned");
-  static bool attr_done = false;
-  if (!attr_done) {
-    CK_CUDA(cudaFuncSetAttribute(ck_oz_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM));
-    attr_done = true;
+  {
+    static bool attr_done[64] = {};  // the attribute is per device
+    int dev = 0;
+    CK_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+      CK_CUDA(cudaFuncSetAttribute(ck_oz_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM));
+      if (dev >= 0 && dev < 64) attr_done[dev] = true;
+    }
   }
   OzGemmArgs g;
   g.a = static_cast<const uint8_t*>(a_slices);
