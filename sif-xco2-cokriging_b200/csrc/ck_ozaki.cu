@@ -126,7 +126,8 @@ __device__ __forceinline__ uint32_t umma_idesc_i8(int n) {
 // Split: FP64 panel rows -> 7 int8 digit slices in the two operand formats + per-row scale 2^(e-7)
 //   A format (128-row blocks):  [rb][kc][p][ku][row group 16][row 8][16 B]
 //   B format ( 64-row blocks):  [hb][kc][ku][q][row group 8][row 8][16 B]
-// One CTA = 8 rows (one row group), one warp per row, a lane owns the 16-element k units lane and lane + 32.
+// One CTA = 8 rows (one row group), one warp per row, a lane owns the 16-element k units lane and lane + 32; the digit
+// bytes go through a shared-memory staging area so that global memory only sees full 128-byte lines.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) ck_oz_split_kernel(const double* __restrict__ src, long long ld, long long rows, int K,
                                                           uint8_t* __restrict__ fa, uint8_t* __restrict__ fb,
@@ -172,8 +173,7 @@ __global__ void __launch_bounds__(256) ck_oz_split_kernel(const double* __restri
   const double up = __hiloint2double((1023 + OZ_QBITS - ex) << 20, 0);  // 2^(55 - ex), exact scaling
   if (lane == 0) scales[row] = (live && amax > 0.0) ? __hiloint2double((1023 + ex - 7) << 20, 0) : 0.0;
 
-  const long long rb = row >> 7, hb = row >> 6;
-  const int rg16 = (int)(row & 127) >> 3, rg8 = (int)(row & 63) >> 3, r8 = (int)(row & 7);
+  extern __shared__ __align__(16) uint8_t stage[];  // units x 7 lines of 128 B
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int u = lane + 32 * h;
@@ -193,19 +193,30 @@ __global__ void __launch_bounds__(256) ck_oz_split_kernel(const double* __restri
         wd[p][i >> 2] |= (uint32_t)(d & 255) << (8 * (i & 3));
       }
     }
-    const int kc = u >> 1, ku = u & 1;
-    if (fa) {
-      uint8_t* base = fa + ((size_t)(rb * kcn + kc)) * OZ_A_STAGE + ku * 2048 + rg16 * 128 + r8 * 16;
+    // stage the 7 x 16 digit bytes of this (row, unit) in shared memory in output order: line (u, p) = 8 rows x 16 B,
+    // the 16-byte slot of row w XOR-swizzled with u so that the warp's 32 stores (same w, 32 units) spread over all banks
 #pragma unroll
-      for (int p = 0; p < OZ_S; ++p)
-        *reinterpret_cast<uint4*>(base + p * OZ_A_SLICE) = make_uint4(wd[p][0], wd[p][1], wd[p][2], wd[p][3]);
-    }
-    if (fb && row < rows_b_pad) {
-      uint8_t* base = fb + ((size_t)(hb * kcn + kc)) * OZ_B_STAGE + ku * OZ_B_KU + rg8 * 128 + r8 * 16;
-#pragma unroll
-      for (int p = 0; p < OZ_S; ++p)
-        *reinterpret_cast<uint4*>(base + p * (OZ_TN * 16)) = make_uint4(wd[p][0], wd[p][1], wd[p][2], wd[p][3]);
-    }
+    for (int p = 0; p < OZ_S; ++p)
+      *reinterpret_cast<uint4*>(stage + ((size_t)(u * OZ_S + p) * 8 + (w ^ (u & 7))) * 16) =
+          make_uint4(wd[p][0], wd[p][1], wd[p][2], wd[p][3]);
+  }
+  __syncthreads();
+  // copy out: every 128-byte line (8 rows of one 16-byte k unit of one slice) is one contiguous piece of both operand
+  // formats; 8 threads move one line, a warp writes four full lines per instruction
+  const int lines = units * OZ_S;
+  const long long row0 = (long long)blockIdx.x * 8;
+  const long long rb = row0 >> 7, hb = row0 >> 6;
+  const int rg16 = (int)(row0 & 127) >> 3, rg8 = (int)(row0 & 63) >> 3;
+  const int sub = threadIdx.x & 7;
+  for (int ln = threadIdx.x >> 3; ln < lines; ln += 32) {
+    const int u = ln / OZ_S, p = ln - u * OZ_S, kc = u >> 1, ku = u & 1;
+    const uint4 v = *reinterpret_cast<const uint4*>(stage + ((size_t)ln * 8 + (sub ^ (u & 7))) * 16);
+    if (fa)
+      *reinterpret_cast<uint4*>(fa + ((size_t)(rb * kcn + kc)) * OZ_A_STAGE + (size_t)p * OZ_A_SLICE + ku * 2048 + rg16 * 128 +
+                                sub * 16) = v;
+    if (fb && row0 < rows_b_pad)
+      *reinterpret_cast<uint4*>(fb + ((size_t)(hb * kcn + kc)) * OZ_B_STAGE + ku * OZ_B_KU + p * (OZ_TN * 16) + rg8 * 128 +
+                                sub * 16) = v;
   }
 }
 
@@ -487,7 +498,17 @@ extern "C" int ck_oz_split(const double* src, ck_i64 ld, ck_i64 rows, ck_i64 k, 
   const ck_i64 rows_pad = ck_oz_scales_len(rows);
   const ck_i64 rows_b_pad = ((rows + OZ_TN - 1) / OZ_TN) * OZ_TN;
   const int vec = ((((uintptr_t)src) & 15) == 0 && (ld & 1) == 0) ? 1 : 0;
-  ck_oz_split_kernel<<<(unsigned)(rows_pad / 8), 256, 0, ck_stream(stream)>>>(src, ld, rows, (int)k, static_cast<uint8_t*>(fmt_a),
+  const size_t smem = (size_t)(k / 16) * OZ_S * 128;  // <= 56 KB
+  {
+    static bool attr_done[64] = {};
+    int dev = 0;
+    CK_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+      CK_CUDA(cudaFuncSetAttribute(ck_oz_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * OZ_S * 128));
+      if (dev >= 0 && dev < 64) attr_done[dev] = true;
+    }
+  }
+  ck_oz_split_kernel<<<(unsigned)(rows_pad / 8), 256, smem, ck_stream(stream)>>>(src, ld, rows, (int)k, static_cast<uint8_t*>(fmt_a),
                                                                             static_cast<uint8_t*>(fmt_b), rows_b_pad, scales, vec);
   CK_LAUNCH_CHECK();
   return CK_OK;
