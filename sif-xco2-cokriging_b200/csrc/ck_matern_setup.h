@@ -73,6 +73,18 @@ static inline int ck_matern_setup(CkMatern* P, double scale, double nu, double l
   P->gam2 = (double)even;               // (1/G(1-mu) + 1/G(1+mu)) / 2
   P->gampl = (double)(even + mu * odd); // 1/Gamma(1+mu)
   P->gammi = (double)(even - mu * odd); // 1/Gamma(1-mu)
+  for (int i = 0; i < CK_KNU_TT; ++i) {
+    const long double fi = (long double)i;
+    P->t_rq[i] = i ? (double)(1.0L / (fi * fi - m2)) : 0.0;
+    P->t_ri[i] = i ? (double)(1.0L / fi) : 0.0;
+    P->t_rm[i] = i ? (double)(1.0L / (fi - mu)) : 0.0;
+    P->t_rp[i] = i ? (double)(1.0L / (fi + mu)) : 0.0;
+  }
+  for (int i = 0; i < CK_KNU_CT; ++i) {
+    const long double ai = -(0.25L - m2) - (long double)i * (long double)(i - 1);  // a after the step-i decrement
+    P->c_ra[i] = i >= 2 ? (double)(1.0L / ai) : 0.0;
+    P->c_cc[i] = i >= 2 ? (double)(-ai / (long double)i) : 0.0;
+  }
   const long double pm = 3.14159265358979323846264338327950288L * mu;
   P->pimu = (fabsl(pm) < 1.0e-9L) ? 1.0 : (double)(pm / sinl(pm));
   return 0;

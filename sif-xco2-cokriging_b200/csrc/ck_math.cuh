@@ -91,6 +91,8 @@ CK_HD double ck_dist(const CkPoint& p, const CkPoint& q) {
 }
 
 // ------------------------------------------------------------------------------------------------
+#define CK_KNU_TT 24  /* Temme terms with tabulated reciprocals (x <= 2 converges in <= 13) */
+#define CK_KNU_CT 64  /* continued-fraction steps with tabulated reciprocals */
 // Matern parameters for one (i, j) block; filled on the host by ck_matern_setup (ck_matern_setup.h).
 struct CkMatern {
   double scale;      // sigma_i^2  or  rho_ij * prod(sigma)
@@ -108,6 +110,14 @@ struct CkMatern {
   double pimu;          // pi mu / sin(pi mu)
   int nl;
   int mode;  // CK_NU_*
+  // reciprocal tables of the K_nu iterations (depend on mu and the iteration index only; filled by ck_matern_setup):
+  // they replace 4 of the 4 divisions per Temme term and 2 of the 3 per continued-fraction step by multiplications
+  double t_rq[CK_KNU_TT];   // 1 / (i^2 - mu^2)
+  double t_ri[CK_KNU_TT];   // 1 / i
+  double t_rm[CK_KNU_TT];   // 1 / (i - mu)
+  double t_rp[CK_KNU_TT];   // 1 / (i + mu)
+  double c_ra[CK_KNU_CT];   // 1 / a_i,  a_i = -(1/4 - mu^2) - i (i - 1)
+  double c_cc[CK_KNU_CT];   // -a_i / i
 };
 
 #define CK_KNU_EPS 1.0e-16
@@ -133,10 +143,17 @@ CK_HD double ck_besselk(const CkMatern& P, double x) {
     double sum1 = p;
     for (int i = 1; i <= CK_KNU_MAXIT; ++i) {
       const double fi = (double)i;
-      ff = (fi * ff + p + q) / (fi * fi - mu2);
-      c *= d / fi;
-      p /= (fi - mu);
-      q /= (fi + mu);
+      if (i < CK_KNU_TT) {
+        ff = (fi * ff + p + q) * P.t_rq[i];
+        c *= d * P.t_ri[i];
+        p *= P.t_rm[i];
+        q *= P.t_rp[i];
+      } else {
+        ff = (fi * ff + p + q) / (fi * fi - mu2);
+        c *= d / fi;
+        p /= (fi - mu);
+        q /= (fi + mu);
+      }
       const double del = c * ff;
       sum += del;
       sum1 += c * (p - fi * ff);
@@ -155,8 +172,14 @@ CK_HD double ck_besselk(const CkMatern& P, double x) {
     double s = 1.0 + q * delh;
     for (int i = 2; i <= CK_KNU_MAXIT; ++i) {
       a -= 2.0 * (double)(i - 1);
-      c = -a * c / (double)i;
-      const double qnew = (q1 - b * q2) / a;
+      double qnew;
+      if (i < CK_KNU_CT) {
+        c *= P.c_cc[i];
+        qnew = (q1 - b * q2) * P.c_ra[i];
+      } else {
+        c = -a * c / (double)i;
+        qnew = (q1 - b * q2) / a;
+      }
       q1 = q2;
       q2 = qnew;
       q += c * qnew;
