@@ -93,9 +93,10 @@ __global__ void __launch_bounds__(K1_THREADS, (MODE == CK_NU_GENERIC && VALUE) ?
       if (r0 + lr < n1 && c0 + lc < n2) {
         if (VALUE && MODE != CK_NU_GENERIC) {  // assembly, closed-form orders: branch-free fast math (ck_math.cuh)
           val = ck_matern_cov_fast<MODE>(P, ck_dist_fast<METRIC>(pr[lr], pc[lc]));
-        } else {
-          const double d = ck_dist<METRIC>(pr[lr], pc[lc]);
-          val = VALUE ? ck_matern_cov<MODE>(P, d) : d;
+        } else if (VALUE) {  // assembly, generic order: fast distance, K_nu by series / continued fraction
+          val = ck_matern_cov<MODE>(P, ck_dist_fast<METRIC>(pr[lr], pc[lc]));
+        } else {             // distance output: reference operation order (bit-identical Euclidean distances)
+          val = ck_dist<METRIC>(pr[lr], pc[lc]);
         }
       }
       v[r][c] = val;

@@ -120,6 +120,19 @@ struct CkMatern {
   double c_cc[CK_KNU_CT];   // -a_i / i
 };
 
+// reciprocal inside the continued fraction: approximate reciprocal + two Newton steps on the device (<= 1 ulp; the
+// recurrence is self-correcting), IEEE division on the host
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ double ck_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(fma(-x, r, 1.0), r, r);
+  return fma(fma(-x, r, 1.0), r, r);
+}
+#define CK_RCP(x) ck_rcp((x))
+#else
+#define CK_RCP(x) (1.0 / (x))
+#endif
 #define CK_KNU_EPS 1.0e-16
 #define CK_KNU_MAXIT 400
 
@@ -184,7 +197,7 @@ CK_HD double ck_besselk(const CkMatern& P, double x) {
       q2 = qnew;
       q += c * qnew;
       b += 2.0;
-      d = 1.0 / (b + a * d);
+      d = CK_RCP(b + a * d);
       delh = (b * d - 1.0) * delh;
       h += delh;
       const double dels = q * delh;
