@@ -35,6 +35,32 @@ static const double CK_RGAMMA1P[27] = {
     -1.181259301697458769513765e-16,
     1.186692254751600332579777e-18};
 
+// g_mu(x) = sqrt(x) e^x K_mu(x) and g_(mu+1)(x) for x >= 2 by Steed's continued fraction (CF2) in long double: the
+// node values of the Chebyshev fits below (no exponential involved, so nodes at x ~ 2500 are as accurate as at x = 2)
+static inline void ck_knu_cf2_nodes(long double mu, long double x, long double* g0, long double* g1) {
+  const long double a1 = 0.25L - mu * mu;
+  long double b = 2.0L * (1.0L + x), d = 1.0L / b, h = d, delh = d, q1 = 0.0L, q2 = 1.0L;
+  long double q = a1, c = a1, a = -a1, s = 1.0L + q * delh;
+  for (int i = 2; i <= 5000; ++i) {
+    a -= 2.0L * (long double)(i - 1);
+    c = -a * c / (long double)i;
+    const long double qnew = (q1 - b * q2) / a;
+    q1 = q2;
+    q2 = qnew;
+    q += c * qnew;
+    b += 2.0L;
+    d = 1.0L / (b + a * d);
+    delh = (b * d - 1.0L) * delh;
+    h += delh;
+    const long double dels = q * delh;
+    s += dels;
+    if (fabsl(dels) < fabsl(s) * 1.0e-19L) break;
+  }
+  h = a1 * h;
+  *g0 = sqrtl(1.57079632679489661923132169163975144L) / s;
+  *g1 = *g0 * (mu + x + 0.5L - h) / x;
+}
+
 // returns 0 on success, -1 on invalid parameters
 static inline int ck_matern_setup(CkMatern* P, double scale, double nu, double len_scale, double nugget) {
   if (!(nu > 0.0) || !(len_scale > 0.0) || !(nu < 1.0e3)) return -1;
@@ -84,6 +110,26 @@ static inline int ck_matern_setup(CkMatern* P, double scale, double nu, double l
     const long double ai = -(0.25L - m2) - (long double)i * (long double)(i - 1);  // a after the step-i decrement
     P->c_ra[i] = i >= 2 ? (double)(1.0L / ai) : 0.0;
     P->c_cc[i] = i >= 2 ? (double)(-ai / (long double)i) : 0.0;
+  }
+  P->cheb_ok = 0;
+  if (P->mode == CK_NU_GENERIC) {
+    static const double seg_lo[3] = {0.0, 0.25, 0.5}, seg_hi[3] = {0.25, 0.5, 1.0};
+    const long double pi = 3.14159265358979323846264338327950288L;
+    for (int sg = 0; sg < 3; ++sg) {
+      long double y[2][CK_KNU_CN];
+      for (int k = 0; k < CK_KNU_CN; ++k) {
+        const long double node = cosl(pi * ((long double)k + 0.5L) / CK_KNU_CN);
+        const long double t = 0.5L * (seg_lo[sg] + seg_hi[sg]) + 0.5L * (seg_hi[sg] - seg_lo[sg]) * node;
+        ck_knu_cf2_nodes(mu, 2.0L / t, &y[0][k], &y[1][k]);
+      }
+      for (int o = 0; o < 2; ++o)
+        for (int j = 0; j < CK_KNU_CN; ++j) {
+          long double acc = 0.0L;
+          for (int k = 0; k < CK_KNU_CN; ++k) acc += y[o][k] * cosl(pi * (long double)j * ((long double)k + 0.5L) / CK_KNU_CN);
+          P->cheb[o][sg][j] = (double)((j == 0 ? 1.0L : 2.0L) * acc / CK_KNU_CN);
+        }
+    }
+    P->cheb_ok = 1;
   }
   const long double pm = 3.14159265358979323846264338327950288L * mu;
   P->pimu = (fabsl(pm) < 1.0e-9L) ? 1.0 : (double)(pm / sinl(pm));

@@ -93,6 +93,7 @@ CK_HD double ck_dist(const CkPoint& p, const CkPoint& q) {
 // ------------------------------------------------------------------------------------------------
 #define CK_KNU_TT 24  /* Temme terms with tabulated reciprocals (x <= 2 converges in <= 13) */
 #define CK_KNU_CT 64  /* continued-fraction steps with tabulated reciprocals */
+#define CK_KNU_CN 14  /* Chebyshev coefficients per segment and order (x > 2) */
 // Matern parameters for one (i, j) block; filled on the host by ck_matern_setup (ck_matern_setup.h).
 struct CkMatern {
   double scale;      // sigma_i^2  or  rho_ij * prod(sigma)
@@ -118,6 +119,11 @@ struct CkMatern {
   double t_rp[CK_KNU_TT];   // 1 / (i + mu)
   double c_ra[CK_KNU_CT];   // 1 / a_i,  a_i = -(1/4 - mu^2) - i (i - 1)
   double c_cc[CK_KNU_CT];   // -a_i / i
+  // x > 2: Chebyshev expansions in t = 2 / x of g_o(t) = sqrt(x) e^x K_o(x), o = mu and mu + 1, on the three segments
+  // t in [0, 1/4], [1/4, 1/2], [1/2, 1] (x >= 8, 4..8, 2..4); CK_KNU_CN coefficients each reach ~2e-15 (tools/cheb_knu.py).
+  // Fitted per block on the host from the continued fraction (ck_matern_setup); cheb_ok = 0 selects the continued fraction.
+  double cheb[2][3][CK_KNU_CN];
+  int cheb_ok;
 };
 
 // reciprocal inside the continued fraction: approximate reciprocal + two Newton steps on the device (<= 1 ulp; the
@@ -174,6 +180,24 @@ CK_HD double ck_besselk(const CkMatern& P, double x) {
     }
     rkmu = sum;
     rk1 = sum1 * xi2;
+  } else if (P.cheb_ok) {  // Chebyshev expansions of sqrt(x) e^x K(x) in t = 2 / x (Clenshaw, both orders at once)
+    const double t = 2.0 * xi;
+    const int seg = t <= 0.25 ? 0 : (t <= 0.5 ? 1 : 2);
+    const double u = seg == 2 ? fma(4.0, t, -3.0) : fma(8.0, t, seg == 0 ? -1.0 : -3.0);
+    const double u2 = 2.0 * u;
+    double b1 = 0.0, b2 = 0.0, d1 = 0.0, d2 = 0.0;
+#pragma unroll
+    for (int j = CK_KNU_CN - 1; j >= 1; --j) {
+      const double nb = fma(u2, b1, P.cheb[0][seg][j] - b2);
+      const double nd = fma(u2, d1, P.cheb[1][seg][j] - d2);
+      b2 = b1; b1 = nb;
+      d2 = d1; d1 = nd;
+    }
+    const double g0 = fma(u, b1, P.cheb[0][seg][0] - b2);
+    const double g1 = fma(u, d1, P.cheb[1][seg][0] - d2);
+    const double w = exp(-x) * sqrt(xi);  // e^-x / sqrt(x)
+    rkmu = g0 * w;
+    rk1 = g1 * w;
   } else {  // Steed's algorithm, continued fraction CF2
     double b = 2.0 * (1.0 + x);
     double d = 1.0 / b;
