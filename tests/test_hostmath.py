@@ -131,3 +131,16 @@ def test_fast_matern_vs_reference_fixture(hostmath):
     got = hostmath.matern_cov_fast(2.0, 1.5, 10.0, 0.25, h)
     assert got[0] == 2.25 and got[2] == 2.0 and got[3] == 0.0
     assert got[1] == pytest.approx(hostmath.matern_cov(2.0, 1.5, 10.0, 0.25, h)[1], rel=1e-15)
+
+
+def test_besselk_chebyshev_branch_vs_mpmath(hostmath):
+    """x > 2, generic nu: per-block Chebyshev expansions of sqrt(x) e^x K(x) in 2 / x fitted from the continued fraction
+    (csrc/ck_matern_setup.h); segment boundaries x = 2, 4, 8 and the far tail included."""
+    mp = pytest.importorskip("mpmath")
+    mp.mp.dps = 40
+    rng = np.random.default_rng(3)
+    x = np.concatenate([rng.uniform(2.0001, 4, 60), rng.uniform(4, 8, 60), rng.uniform(8, 60, 60), 10 ** rng.uniform(1.8, 2.8, 40),
+                        [2.0000001, 3.9999999, 4.0, 4.0000001, 7.9999999, 8.0, 8.0000001, 690.0]])
+    for nu in (0.05, 0.2, 0.39, 0.75, 0.82, 1.0, 1.25, 1.49, 2.0, 2.3, 3.0, 3.2, 7.7):
+        truth = np.array([float(mp.besselk(nu, mp.mpf(float(v)))) for v in x])
+        assert relerr(hostmath.besselk(nu, x), truth) < 2e-15, nu
