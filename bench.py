@@ -327,11 +327,10 @@ def run_gpu(args, n_per_var: int, m: int) -> None:
                                     "frac_of_2x_bf16_burst": int8_ops_launch / launch_ms / 1e9 / (2 * bf16_burst),
                                     "fp64_equiv_TFs": int8_ops_launch / 28 / launch_ms / 1e9},
                 "fp64_equiv_TFs": achieved_tf, "dgemm_live_TFs": dgemm_tf, "fp64_equiv_over_dgemm": achieved_tf / dgemm_tf,
-                # ncu of this launch shape (rows = 38976, lower, K = 1024; profiles/r01z_ozgemm_ncu_full_summary.txt and the
-                # dram-bytes pass of tools/gpu_a4.sh with the 16-row-block tile order): dram read 22.13 GB + write 6.07 GB;
-                # algorithmic 12.15 GB of C (read + write) + 0.56 GB of slices
-                "traffic": 28.2e9, "traffic_note": "per launch at rows=38976 (ncu), algorithmic 12.7e9: the operand slices are "
-                                                   "re-read ~14x from DRAM (L2 hit rate 76 %)",
+                # ncu --set full of this launch shape (rows = 38976, lower, K = 1024; profiles/r01ai_ozgemm_ncu_full_summary.txt):
+                # dram read 21.79 GB + write 6.08 GB; algorithmic 12.15 GB of C (read + write) + 0.56 GB of slices
+                "traffic": 27.86e9, "traffic_note": "per launch at rows=38976 (ncu r01ai), algorithmic 12.7e9: the operand slices "
+                                                    "are re-read ~14x from DRAM (L2 hit rate 76 %)",
                 "flops_per_step": fp64_flops}
         else:
             roofline = {"bound": "tensor", "kernel": "ck_gemm_nt_kernel (FP64 DMMA: DSYRK trailing + TRSM updates)",
