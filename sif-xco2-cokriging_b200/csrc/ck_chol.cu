@@ -922,6 +922,76 @@ extern "C" int ck_potrf(double* a, ck_i64 n, ck_i64 ld, void* ws, int* info, voi
   return CK_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Few right-hand sides (the likelihood objective solves with ONE): the update R[:, k1:] -= V[:, k0:k1] L[k1:, k0:k1]^T is a
+// matrix-vector product per right-hand side -- HBM-bound (every entry of L is read once), so it is a streaming kernel, not a
+// DMMA GEMM on a 128 x 64 tile with one valid row.  One warp per row j of L: lane-strided partial sums over the K <= 1024
+// columns (16-byte loads), fixed xor-shuffle tree => deterministic.  V[:, k0:k1] sits in shared memory.
+// ------------------------------------------------------------------------------------------------
+constexpr int TRSV_MAX_RHS = 8;
+template <int NR>
+__global__ void __launch_bounds__(256) ck_trsv_update_kernel(const double* __restrict__ lpan, long long ld, long long rows, int kk,
+                                                             double* __restrict__ rhs, long long ld_rhs, long long k0,
+                                                             long long k1, int vec) {
+  extern __shared__ double vs[];  // [NR][kk]
+  for (int i = threadIdx.x; i < NR * kk; i += 256) vs[i] = rhs[(long long)(i / kk) * ld_rhs + k0 + (i % kk)];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (long long j = (long long)blockIdx.x * 8 + warp; j < rows; j += (long long)gridDim.x * 8) {
+    const double* lrow = lpan + j * ld;
+    double acc[NR];
+#pragma unroll
+    for (int c = 0; c < NR; ++c) acc[c] = 0.0;
+    if (vec) {
+      for (int k = 2 * lane; k < kk; k += 64) {
+        const double2 lv = *reinterpret_cast<const double2*>(lrow + k);
+#pragma unroll
+        for (int c = 0; c < NR; ++c) acc[c] = fma(lv.y, vs[c * kk + k + 1], fma(lv.x, vs[c * kk + k], acc[c]));
+      }
+    } else {
+      for (int k = lane; k < kk; k += 32) {
+        const double lv = lrow[k];
+#pragma unroll
+        for (int c = 0; c < NR; ++c) acc[c] = fma(lv, vs[c * kk + k], acc[c]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < NR; ++c) {
+      double a = acc[c];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (lane == 0) rhs[(long long)c * ld_rhs + k1 + j] -= a;
+    }
+  }
+}
+
+static int trsv_update_launch(const double* lpan, ck_i64 ld, ck_i64 rows, ck_i64 kk, double* rhs, ck_i64 ld_rhs, ck_i64 nrhs,
+                              ck_i64 k0, ck_i64 k1, cudaStream_t st) {
+  const int vec = ((((uintptr_t)lpan) & 15) == 0 && (ld & 1) == 0 && (kk & 1) == 0) ? 1 : 0;
+  long long blocks = (rows + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  const size_t smem = (size_t)nrhs * kk * sizeof(double);  // <= 8 x 1024 x 8 B = 64 KB
+#define CK_TRSV(NR)                                                                                                    \
+  case NR: {                                                                                                           \
+    static bool attr_done[64] = {};                                                                                    \
+    int dev = 0;                                                                                                       \
+    CK_CUDA(cudaGetDevice(&dev));                                                                                      \
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {                                                                     \
+      CK_CUDA(cudaFuncSetAttribute(ck_trsv_update_kernel<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize,             \
+                                   NR * 1024 * (int)sizeof(double)));                                                  \
+      if (dev >= 0 && dev < 64) attr_done[dev] = true;                                                                 \
+    }                                                                                                                  \
+    ck_trsv_update_kernel<NR><<<(unsigned)blocks, 256, smem, st>>>(lpan, ld, rows, (int)kk, rhs, ld_rhs, k0, k1, vec); \
+  } break;
+  switch ((int)nrhs) {
+    CK_TRSV(1) CK_TRSV(2) CK_TRSV(3) CK_TRSV(4) CK_TRSV(5) CK_TRSV(6) CK_TRSV(7) CK_TRSV(8)
+    default: CK_REQUIRE(false, "trsv path needs 1..8 right-hand sides");
+  }
+#undef CK_TRSV
+  CK_LAUNCH_CHECK();
+  return CK_OK;
+}
+
 struct TrsmCtx {
   const double* l; ck_i64 n, ld; const double* xinv; double* rhs; ck_i64 nrhs, ldr; cudaStream_t st;
   ck_i64 s(ck_i64 b) const { return b * CK_NB < n ? b * CK_NB : n; }
@@ -966,6 +1036,18 @@ extern "C" int ck_trsm_lower(const double* l, ck_i64 n, ck_i64 ld, const void* w
   const ck_i64 nblk = (n + CK_NB - 1) / CK_NB;
   const int agg = agg_blocks();
   int rc;
+  if (nrhs <= TRSV_MAX_RHS && (ck_i64)agg * CK_NB <= 1024) {
+    // few right-hand sides: per aggregate the small solves on <= 1024 columns (a single-CTA substitution kernel was tried
+    // and is slower: one CTA cannot pull the 4 MB tile fast enough), then one streaming matrix-vector update to the right
+    for (ck_i64 b0 = 0; b0 < nblk; b0 += agg) {
+      const ck_i64 b1 = b0 + agg < nblk ? b0 + agg : nblk;
+      if ((rc = solve_range(c, b0, b1))) return rc;
+      const ck_i64 k0 = c.s(b0), k1 = c.s(b1);
+      if (k1 >= n) break;
+      if ((rc = trsv_update_launch(l + k1 * ld + k0, ld, n - k1, k1 - k0, rhs, ld_rhs, nrhs, k0, k1, st))) return rc;
+    }
+    return CK_OK;
+  }
   if (oz_wanted(n) && (ck_i64)agg * CK_NB <= OZ_KMAX && nrhs >= 1024 && nrhs <= n) {
     // INT8 tensor-core updates (see ck_potrf).  The slice scratch lives behind the block inverses in the
     // factorisation workspace: solves that share one factor must not run concurrently.
