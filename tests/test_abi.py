@@ -46,6 +46,34 @@ def test_host_only_entry_points():
     assert _lib.lib.ck_local_predict_workspace_bytes(10, 100) >= 10 * 102 * 112 * 8
 
 
+def test_int8_path_host_only_entry_points():
+    """Sizes and switches of the INT8 update path are plain host functions (no CUDA call)."""
+    from cokrig_b200 import _lib
+    lib = _lib.lib
+    # slice buffers: 7 digit slices, A format in 128-row blocks, B format in 64-row blocks, k in 32-deep chunks
+    assert lib.ck_oz_slices_bytes(128, 32, 0) == 7 * 128 * 32
+    assert lib.ck_oz_slices_bytes(129, 1024, 0) == 2 * 7 * 128 * 1024
+    assert lib.ck_oz_slices_bytes(64, 32, 1) == 7 * 64 * 32
+    assert lib.ck_oz_slices_bytes(65, 64, 1) == 2 * 7 * 64 * 64
+    assert lib.ck_oz_slices_bytes(0, 1024, 0) == 0
+    assert lib.ck_oz_scales_len(1) == 128 and lib.ck_oz_scales_len(129) == 256
+    # the factorisation workspace carries the slice scratch from n = 2048 on, whatever the switches say
+    xinv = lambda n: ((n + 127) // 128) * 128 * 128 * 8  # noqa: E731
+    assert lib.ck_potrf_workspace_bytes(2047) == xinv(2047)
+    big = lib.ck_potrf_workspace_bytes(4096)
+    assert big >= xinv(4096) + lib.ck_oz_slices_bytes(4096, 1024, 0) + lib.ck_oz_slices_bytes(4096, 1024, 1) + 2 * 8 * 4096
+    lib.ck_oz_configure(0, -1)
+    try:
+        assert lib.ck_potrf_workspace_bytes(4096) == big and lib.ck_oz_active(1 << 20) == 0
+    finally:
+        lib.ck_oz_configure(1, -1)
+    assert lib.ck_oz_active(1 << 20) == 1 and lib.ck_oz_active(2047) == 0
+    assert lib.ck_oz_set_grid(100) == 0 and lib.ck_oz_set_grid(0) == 0
+    # argument checks come before any CUDA call
+    assert lib.ck_oz_split(None, 0, 4, 48, None, None, None, None) == _lib.CK_ERR_ARG
+    assert lib.ck_oz_gemm(None, None, 4, None, None, 4, 32, None, 4, 0, None) == _lib.CK_ERR_ARG
+
+
 def test_argument_validation_without_gpu():
     """Bad arguments are rejected before any CUDA call, with a message."""
     from cokrig_b200 import _lib
