@@ -171,9 +171,8 @@ def run_gpu(args, n_per_var: int, m: int) -> None:
         raise RuntimeError("bench.py needs a CUDA device; the product has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # keep stdout to the one JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # keep stdout to the one JSON line: NCCL writes its version banner / debug lines to stdout unless told otherwise
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from cokrig_b200 import METRIC_HAVERSINE, _lib, ops
     import fields, joint_prediction, model
