@@ -171,9 +171,19 @@ def run_gpu(args, n_per_var: int, m: int) -> None:
         raise RuntimeError("bench.py needs a CUDA device; the product has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # keep stdout to the one JSON line: NCCL writes its version banner / debug lines to stdout unless told otherwise
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # keep stdout to the one JSON line: the NCCL version banner is written to fd 1 when the communicator is created,
+        # so communicator creation (init + first collective) runs with fd 1 pointing at stderr
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     from cokrig_b200 import METRIC_HAVERSINE, _lib, ops
     import fields, joint_prediction, model
 
