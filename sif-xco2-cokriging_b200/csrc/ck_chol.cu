@@ -601,7 +601,7 @@ __global__ void ck_nll_combine_kernel(double* out, long long n) {
 // everywhere; CK_OZ_MIN_ROWS is the smallest trailing dimension handed to the INT8 kernel (below it the
 // persistent kernel cannot fill the machine and the DMMA kernel is used).
 // ------------------------------------------------------------------------------------------------
-static int agg_blocks_fwd();
+static int agg_blocks();
 static int g_oz_enabled = -1;
 static ck_i64 g_oz_min_rows = -1;
 static int oz_enabled() {
@@ -670,7 +670,7 @@ static OzScratch oz_scratch(void* ws, ck_i64 n) {
   return s;
 }
 
-extern "C" int ck_oz_active(ck_i64 n) { return (oz_wanted(n) && (ck_i64)agg_blocks_fwd() * CK_NB <= OZ_KMAX) ? 1 : 0; }
+extern "C" int ck_oz_active(ck_i64 n) { return (oz_wanted(n) && (ck_i64)agg_blocks() * CK_NB <= OZ_KMAX) ? 1 : 0; }
 
 extern "C" size_t ck_potrf_workspace_bytes(ck_i64 n) {
   if (n <= 0) return 0;
@@ -704,8 +704,6 @@ static int potf2_launch(double* a, long long ld, int nb, double* x, int* info, i
 // an aggregate: panels are factored 128 columns at a time, but the O(N^3) trailing update is applied
 // once per aggregate with K = 128 * CK_AGG, which halves (quarters, ...) the number of passes over the
 // trailing matrix and amortises each tile's prologue/epilogue over a longer DMMA main loop.
-static int agg_blocks();
-static int agg_blocks_fwd() { return agg_blocks(); }
 static int agg_blocks() {
   static int v = 0;
   if (v == 0) {
