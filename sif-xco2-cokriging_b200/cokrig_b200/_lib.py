@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_double, c_int, c_int64, c_size_t, c_ulonglong, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_int, c_int64, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("COKRIG_B200_LIB", os.path.join(_HERE, "libcokrig_b200.so"))

@@ -20,7 +20,6 @@ partitioning, communication order and reductions without a GPU.
 """
 from __future__ import annotations
 
-import contextlib
 import os
 from typing import Callable, List, Optional, Sequence, Tuple
 
