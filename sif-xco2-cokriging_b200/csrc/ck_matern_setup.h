@@ -3,6 +3,7 @@
 // (tests/hostmath).  Parameter meaning follows src/model.py:188-207 of the reference.
 #pragma once
 #include <math.h>
+#include <string.h>
 #include "ck_math.cuh"
 
 // Taylor coefficients of 1/Gamma(1+z) about z = 0 (generated with mpmath at 40 digits).
@@ -113,22 +114,45 @@ static inline int ck_matern_setup(CkMatern* P, double scale, double nu, double l
   }
   P->cheb_ok = 0;
   if (P->mode == CK_NU_GENERIC) {
-    static const double seg_lo[3] = {0.0, 0.25, 0.5}, seg_hi[3] = {0.25, 0.5, 1.0};
-    const long double pi = 3.14159265358979323846264338327950288L;
-    for (int sg = 0; sg < 3; ++sg) {
-      long double y[2][CK_KNU_CN];
-      for (int k = 0; k < CK_KNU_CN; ++k) {
-        const long double node = cosl(pi * ((long double)k + 0.5L) / CK_KNU_CN);
-        const long double t = 0.5L * (seg_lo[sg] + seg_hi[sg]) + 0.5L * (seg_hi[sg] - seg_lo[sg]) * node;
-        ck_knu_cf2_nodes(mu, 2.0L / t, &y[0][k], &y[1][k]);
+    // the fit depends on mu only and costs ~0.4 ms of host time: keep the last few (the three blocks of a bivariate model
+    // are set up again for every assembly, cross-covariance and local-prediction call of one parameter vector)
+    struct ChebCache { double mu; int valid; double cheb[2][3][CK_KNU_CN]; };
+    static thread_local ChebCache cache[8];
+    static thread_local int next_slot = 0;
+    const ChebCache* hit = nullptr;
+    for (int i = 0; i < 8; ++i)
+      if (cache[i].valid && cache[i].mu == (double)mu) hit = &cache[i];
+    if (!hit) {
+      static const double seg_lo[3] = {0.0, 0.25, 0.5}, seg_hi[3] = {0.25, 0.5, 1.0};
+      const long double pi = 3.14159265358979323846264338327950288L;
+      static thread_local long double cosjk[CK_KNU_CN][CK_KNU_CN];
+      static thread_local int cos_ready = 0;
+      if (!cos_ready) {
+        for (int j = 0; j < CK_KNU_CN; ++j)
+          for (int k = 0; k < CK_KNU_CN; ++k) cosjk[j][k] = cosl(pi * (long double)j * ((long double)k + 0.5L) / CK_KNU_CN);
+        cos_ready = 1;
       }
-      for (int o = 0; o < 2; ++o)
-        for (int j = 0; j < CK_KNU_CN; ++j) {
-          long double acc = 0.0L;
-          for (int k = 0; k < CK_KNU_CN; ++k) acc += y[o][k] * cosl(pi * (long double)j * ((long double)k + 0.5L) / CK_KNU_CN);
-          P->cheb[o][sg][j] = (double)((j == 0 ? 1.0L : 2.0L) * acc / CK_KNU_CN);
+      ChebCache* slot = &cache[next_slot];
+      next_slot = (next_slot + 1) % 8;
+      slot->valid = 0;
+      for (int sg = 0; sg < 3; ++sg) {
+        long double y[2][CK_KNU_CN];
+        for (int k = 0; k < CK_KNU_CN; ++k) {
+          const long double t = 0.5L * (seg_lo[sg] + seg_hi[sg]) + 0.5L * (seg_hi[sg] - seg_lo[sg]) * cosjk[1][k];
+          ck_knu_cf2_nodes(mu, 2.0L / t, &y[0][k], &y[1][k]);
         }
+        for (int o = 0; o < 2; ++o)
+          for (int j = 0; j < CK_KNU_CN; ++j) {
+            long double acc = 0.0L;
+            for (int k = 0; k < CK_KNU_CN; ++k) acc += y[o][k] * cosjk[j][k];
+            slot->cheb[o][sg][j] = (double)((j == 0 ? 1.0L : 2.0L) * acc / CK_KNU_CN);
+          }
+      }
+      slot->mu = (double)mu;
+      slot->valid = 1;
+      hit = slot;
     }
+    memcpy(P->cheb, hit->cheb, sizeof(P->cheb));
     P->cheb_ok = 1;
   }
   const long double pm = 3.14159265358979323846264338327950288L * mu;
