@@ -361,6 +361,10 @@ def run_gpu(args, n_per_var: int, m: int) -> None:
             "solve_TFs": wm["solve_flops"] / (phase_ms["solve"] / 1e3) / 1e12,
             "roofline": roofline,
             "update_path": "int8 tcgen05 (FP64-equivalent)" if int8_active else "fp64 dmma",
+            "arithmetic": ("inputs, outputs, assembly, panel factorisation and all accumulation into Sigma / the right-hand sides in "
+                           "f64; the rank-1024 trailing and solve updates as exact int8 x int8 -> int32 products of 7 balanced "
+                           "base-256 digit slices of a 55-bit fixed-point rounding of the f64 operands (error below the f64 "
+                           "rounding of the same product; CK_OZAKI=0 runs them in f64 DMMA)") if int8_active else "f64 throughout",
             "e2e": {"value": world * m / (e2e_ms / args.steps / 1e3), "unit": "predictions/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
                     "api": "joint_prediction.Predictor.predict_frame (host numpy in, DataFrame out)"},
