@@ -126,3 +126,57 @@ def test_wls_cost_helpers():
     assert model._wls(y[[0, 2]], f[[0, 2]], c[[0, 2]]) == pytest.approx(10 * (0.5 / 1.5) ** 2 + 30 * 0.25)
     assert model.MultivariateMatern._weighted_least_squares(y, f, c) == pytest.approx(
         10 * (0.5 / 1.5) ** 2 + 20 * 4.0 + 30 * 0.25)
+
+
+# ------------------------------------------------------------------------------------------------ drop-in boundary
+# helpers of the reference's per-target Python loop that the batched local-neighbourhood kernel replaces as a whole
+# (ck_local_count / ck_local_predict): private, never called from outside point_prediction.Predictor
+_REPLACED_PRIVATE = {"point_prediction.Predictor._pred_cov", "point_prediction.Predictor._local_dist_ix",
+                     "point_prediction.Predictor._local_values", "point_prediction.Predictor._verify_model",
+                     "point_prediction.Predictor._local_prediction"}
+
+
+def _resolve(key: str):
+    """'mod.func' or 'mod.Class.method' in the drop-in modules (inherited methods count), or None."""
+    import importlib
+    parts = key.split(".")
+    obj = importlib.import_module(parts[0])
+    for name in parts[1:]:
+        obj = getattr(obj, name, None)
+        if obj is None:
+            return None
+    return obj if callable(obj) else None
+
+
+def test_every_reference_callable_exists_with_the_same_signature():
+    """Drop-in boundary: every function and method the reference defines in its six modules exists here with
+    the same parameter names, kinds and defaults (fixture dumped from the unmodified reference by
+    tests/golden/make_signatures.py)."""
+    import inspect
+    import json
+    import os
+    from conftest import GOLDEN
+    ref_sigs = json.load(open(os.path.join(GOLDEN, "signatures.json")))
+    assert len(ref_sigs) > 90
+    missing = sorted(k for k in ref_sigs if _resolve(k) is None and k not in _REPLACED_PRIVATE)
+    assert not missing, missing
+    assert all(k.split(".")[-1].startswith("_") for k in _REPLACED_PRIVATE)
+    for key, want in ref_sigs.items():
+        fn = _resolve(key)
+        if fn is None:
+            continue
+        got = [[p.name, p.kind.name, None if p.default is inspect._empty else repr(p.default)]
+               for p in inspect.signature(fn).parameters.values()]
+        assert got == want, key
+
+
+def test_signature_fixture_is_current(ref):
+    """The committed fixture equals what the reference on disk defines (build container only)."""
+    import importlib.util
+    import json
+    import os
+    from conftest import GOLDEN
+    spec = importlib.util.spec_from_file_location("make_signatures", os.path.join(GOLDEN, "make_signatures.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    assert mk.collect(ref) == json.load(open(os.path.join(GOLDEN, "signatures.json")))
