@@ -72,6 +72,73 @@ class Predictor:
                 blocks[f"{i}{j}"] = b.cpu().numpy()
         return blocks
 
+    # ---- the reference's per-target helpers (src/point_prediction.py:115-222), kept with their signatures and return
+    # values for callers that use them directly.  They are NOT on the prediction path (`_predict_chunk` hands all targets
+    # to one batched device call); every number they return still comes from the device: distances from
+    # ck_distance_block, covariances from ck_matern_eval / ck_matern_block, the factorisation from ck_potrf, the local
+    # solve from ck_local_predict with a single target.
+    def _pred_cov(self, dists: list) -> list:
+        """Covariance (own process, with nugget) and cross-covariance vectors for the local distances of one target."""
+        return [self.mod.covariance(self.i, dists[j], use_nugget=True) if j == self.i
+                else self.mod.cross_covariance(self.i, j, dists[j]) for j in range(self.n_procs)]
+
+    def _local_dist_ix(self, s0: np.ndarray, max_dist: float) -> tuple[list, list]:
+        """Per dataset: boolean mask of the data within `max_dist` of `s0` (the datum at `s0` itself excluded from
+        process `i` during cross-validation) and the retained distances."""
+        dists = [distance_matrix(s0, f.coords_main, units=self.dist_units, fast_dist=self.fast_dist) for f in self.mf.fields]
+        keep = [d <= max_dist for d in dists]
+        if self.cv:
+            keep[self.i] = (dists[self.i] > 0) & (dists[self.i] <= max_dist)
+        return [k.squeeze() for k in keep], [d[k] for d, k in zip(dists, keep)]
+
+    def _local_values(self, s0: np.ndarray, max_dist: float) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """(local covariance vector, local covariance matrix, local data vector) for the target `s0`."""
+        ix, local_dists = self._local_dist_ix(s0, max_dist)
+        local_data = np.hstack([np.asarray(self.mf.fields[i].values_main)[ix[i]] for i in range(self.n_procs)])
+        rows = []
+        for i in range(self.n_procs):
+            row = []
+            for j in range(self.n_procs):
+                blk = self.Sigma[f"{i}{j}"][np.ix_(ix[i], ix[j])] if i <= j else self.Sigma[f"{j}{i}"][np.ix_(ix[j], ix[i])].T
+                row.append(blk)
+            rows.append(row)
+        local_cov = np.block(rows)
+        assert local_data.shape[0] == local_cov.shape[0]
+        return np.hstack(self._pred_cov(local_dists)), local_cov, local_data
+
+    def _verify_model(self, c0: float, local_pred_cov: np.ndarray, local_cov: np.ndarray):
+        """Raises LinAlgError unless [[c0, c^T], [c, Sigma_loc]] is positive definite (device Cholesky)."""
+        from scipy.linalg import LinAlgError
+        aug = np.vstack([np.hstack([c0, local_pred_cov]), np.column_stack([local_pred_cov, local_cov])])
+        factor = ops.potrf(ops.to_device(np.ascontiguousarray(aug, dtype=float)))
+        if factor.info != 0:
+            raise LinAlgError(f"{factor.info}-th leading minor of the array is not positive definite")
+
+    @staticmethod
+    def _pred_calc(c0: float, local_pred_cov: np.ndarray, local_cov: np.ndarray, local_data: np.ndarray) -> tuple[float, float]:
+        """Prediction and standard deviation from explicit local quantities: device Cholesky of `local_cov`, one
+        triangular solve with [c ; z] (v = L^-1 c, y = L^-1 z), pred = v.y, sd = nanmax(sqrt(c0 - v.v), 0); (nan, nan)
+        with a warning if the matrix is not positive definite."""
+        k = int(np.asarray(local_data).size)
+        factor = ops.potrf(ops.to_device(np.ascontiguousarray(local_cov, dtype=float)))
+        if factor.info != 0:
+            warnings.warn("Local covariance matrix not positive definte; returning NaN.")
+            return np.nan, np.nan
+        import torch
+        rhs = torch.empty((2, ops.padded_ld(k)), dtype=torch.float64, device="cuda")[:, :k]
+        rhs.copy_(torch.from_numpy(np.vstack([np.asarray(local_pred_cov, dtype=float).reshape(1, k),
+                                               np.asarray(local_data, dtype=float).reshape(1, k)])))
+        v = factor.solve_lower(rhs).cpu().numpy()
+        with np.errstate(invalid="ignore"):
+            pred_std = np.sqrt(c0 - float(v[0] @ v[0]))
+        return float(v[0] @ v[1]), float(np.nanmax([pred_std, 0.0]))
+
+    def _local_prediction(self, s0: np.ndarray, c0: float, max_dist: float) -> tuple[float, float]:
+        """(prediction, prediction standard deviation) at the single location `s0`."""
+        row = pd.DataFrame(np.atleast_2d(np.asarray(s0, dtype=float))[:, :2], columns=["d1", "d2"])
+        out = self._predict_chunk(row, c0, max_dist)
+        return float(out["pred"].iloc[0]), float(out["pred_err"].iloc[0])
+
     def _predict_chunk(self, df_chunk: pd.DataFrame, c0: float, max_dist: float):
         """Batched local prediction for all rows of `df_chunk` (adds ``pred`` and ``pred_err``)."""
         pc = df_chunk.iloc[:, :2].values.astype(float)

@@ -31,6 +31,8 @@ def collect(ns) -> dict:
                 out[f"{mod}.{name}"] = shape(obj)
             elif inspect.isclass(obj):
                 for mname, meth in vars(obj).items():
+                    if isinstance(meth, (staticmethod, classmethod)):
+                        meth = meth.__func__
                     if inspect.isfunction(meth):
                         out[f"{mod}.{name}.{mname}"] = shape(meth)
     return out

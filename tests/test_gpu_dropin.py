@@ -182,3 +182,36 @@ def test_fit_dropin_matches_reference_cost():
     # L-BFGS-B with finite differences: same basin, cost within 1% of the reference's optimum
     assert fitted.fit_result.cost <= float(g["fit_cost"]) * 1.01
     assert len(fitted.fit_result.df_theoretical) == 300
+
+
+def test_point_predictor_per_target_helpers():
+    """The reference's per-target helper methods (src/point_prediction.py:115-222) exist with their signatures and agree
+    with the batched device path and with the reference fixture: explicit local quantities -> _pred_calc equals
+    _local_prediction (one-target batch) equals the fixture; _verify_model raises only for a non-PD augmented matrix."""
+    import fields, point_prediction
+    from scipy.linalg import LinAlgError
+    g = golden("point_euclid")
+    mf = fields.MultiField.from_arrays([g["coords0"], g["coords1"]], [g["z0"], g["z1"]])
+    P = point_prediction.Predictor(make_model(g["params"]), mf, fast_dist=False, dist_units=None)
+    P.i = 1
+    md = float(g["max_dist"])
+    c0 = P.mod.covariance(1, 0, use_nugget=True)[0]
+    for t in (0, 3, 7):
+        s0 = g["pcoords"][t]
+        ix, dists = P._local_dist_ix(s0, md)
+        assert sum(int(m.sum()) for m in ix) == int(g["k"][t]) and all((d <= md).all() for d in dists)
+        c, S, z = P._local_values(s0, md)
+        assert c.shape == z.shape == (int(g["k"][t]),) and S.shape == (z.size, z.size) and np.allclose(S, S.T, rtol=0, atol=1e-15)
+        P._verify_model(c0, c, S)  # valid model: no exception
+        pred, sd = P._pred_calc(c0, c, S, z)
+        pred_b, sd_b = P._local_prediction(s0, c0, md)
+        assert abs(pred - g["pred"][t]) <= 1e-9 * abs(g["pred"][t]) and abs(sd ** 2 - g["sd"][t] ** 2) < 1e-9
+        assert abs(pred_b - pred) <= 1e-9 * abs(pred) and abs(sd_b ** 2 - sd ** 2) < 1e-9
+    with pytest.raises(LinAlgError):
+        P._verify_model(0.5 * float(c @ np.linalg.solve(S, c)), c, S)  # c0 below c^T S^-1 c: Schur complement negative
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        bad = S.copy()
+        bad[0, 0] = -1.0
+        assert np.isnan(P._pred_calc(c0, c, bad, z)).all()
+    assert any("not positive definte" in str(x.message) for x in w)
