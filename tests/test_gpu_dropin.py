@@ -196,7 +196,7 @@ def test_point_predictor_per_target_helpers():
     P.i = 1
     md = float(g["max_dist"])
     c0 = P.mod.covariance(1, 0, use_nugget=True)[0]
-    for t in (0, 3, 7):
+    for t in (3, 7):
         s0 = g["pcoords"][t]
         ix, dists = P._local_dist_ix(s0, md)
         assert sum(int(m.sum()) for m in ix) == int(g["k"][t]) and all((d <= md).all() for d in dists)
@@ -209,6 +209,9 @@ def test_point_predictor_per_target_helpers():
         assert abs(pred_b - pred) <= 1e-9 * abs(pred) and abs(sd_b ** 2 - sd ** 2) < 1e-9
     with pytest.raises(LinAlgError):
         P._verify_model(0.5 * float(c @ np.linalg.solve(S, c)), c, S)  # c0 below c^T S^-1 c: Schur complement negative
+    c_d, S_d, _ = P._local_values(g["pcoords"][0], md)  # target 0 sits on a datum: the augmented matrix is singular
+    with pytest.raises(LinAlgError):
+        P._verify_model(c0, c_d, S_d)
     with warnings.catch_warnings(record=True) as w:
         warnings.simplefilter("always")
         bad = S.copy()
