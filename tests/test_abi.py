@@ -98,3 +98,29 @@ def test_no_cpu_fallback():
     import model
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         model.MultivariateMatern().covariance(0, np.ones(3))
+
+
+def test_library_contains_blackwell_native_sass():
+    """The shipped library really carries the tcgen05 / TMEM / bulk-copy kernel and the FP64 DMMA kernels (SASS mnemonics:
+    tcgen05.mma kind::i8 -> UTCIMMA, tcgen05.ld -> LDTM, cp.async.bulk -> UBLKCP, mma.sync f64 -> DMMA), for sm_100a only."""
+    import shutil
+    import subprocess
+    from cokrig_b200 import _lib
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    listing = subprocess.run([cuobjdump, "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in listing and "sm_90" not in listing and "sm_80" not in listing
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    sections, cur = {}, None
+    for line in sass.splitlines():
+        if "Function :" in line:
+            cur = line.split("Function :")[1].strip()
+            sections[cur] = []
+        elif cur is not None:
+            sections[cur].append(line)
+    body = lambda key: "\n".join("\n".join(v) for k, v in sections.items() if key in k)  # noqa: E731
+    oz = body("ck_oz_gemm_kernel")
+    for mnemonic in ("UTCIMMA", "LDTM", "UBLKCP", "UTCBAR"):
+        assert mnemonic in oz, mnemonic
+    assert "DMMA" in body("ck_potf2_inv_kernel") and "DMMA" in body("ck_gemm_nt_kernel")
