@@ -311,7 +311,7 @@ def run_gpu(args, n_per_var: int, m: int) -> None:
                 s0, s1 = ev(), ev()
                 s0.record()
                 _lib.check(_lib.lib.ck_oz_gemm(fa.data_ptr(), sc.data_ptr(), rows, fb.data_ptr(), sc.data_ptr(), rows, kk,
-                                               cc.data_ptr(), cc.stride(0), 1, st))
+                                               cc.data_ptr(), cc.stride(0), 1, 0, st))
                 s1.record(); torch.cuda.synchronize()
                 if it >= 2:
                     times.append(s0.elapsed_time(s1))

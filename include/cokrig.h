@@ -210,18 +210,25 @@ int ck_vario_bin_reduce(ck_i64 na, ck_i64 nb, int n_bins, const void* ws_dev, un
 size_t ck_local_predict_workspace_bytes(ck_i64 m, ck_i64 kmax);
 
 /* Pass 1: k_dev[c] = number of data (both processes) within max_dist of target c
- * (cv != 0: data of process i_pred at distance exactly 0 are excluded, src/point_prediction.py:140-142). */
+ * (cv != 0: data of process i_pred at distance exactly 0 are excluded, src/point_prediction.py:140-142), and
+ * seg_dev[8 c .. 8 c + 7] = the same count split by (process, quarter of the index range) -- the offsets pass 2 needs to
+ * compact the neighbours in the reference's order without counting again.  Coordinate arrays 16-byte aligned. */
 int ck_local_count(const double* xy0_dev, ck_i64 n0, const double* xy1_dev, ck_i64 n1, const double* xyp_dev, ck_i64 m,
-                   int n_procs, int i_pred, int metric, double max_dist, int cv, int* k_dev, void* stream);
+                   int n_procs, int i_pred, int metric, double max_dist, int cv, int* k_dev, int* seg_dev, void* stream);
 
-/* Pass 2: for every target: gather neighbours (process 0 then 1, index order), assemble the local
- * covariance from coordinates, factor, solve.  pred/sd follow src/point_prediction.py:200-241:
- * NaN when there is no neighbour or the local matrix is not positive definite (info_dev[c] > 0);
- * sd = sqrt(max(c0 - w.c, 0)) with NaN -> 0.  kmax = max_c k_dev[c] (from pass 1). */
+/* Pass 2: for every target: gather neighbours (process 0 then 1, index order), re-compute the local covariance from
+ * coordinates, factor, solve.  pred/sd follow src/point_prediction.py:200-241: NaN when there is no neighbour or the
+ * local matrix is not positive definite (info_dev[c] > 0); sd = sqrt(max(c0 - w.c, 0)) with NaN -> 0 (info_dev[c] = -1
+ * when c0 - w.c <= 0: the reference's augmented-matrix check fails there and it warns).
+ * params_sigma: the model the local covariance MATRIX is built from (the reference freezes Sigma when the Predictor is
+ * constructed, src/point_prediction.py:42); params_pred (NULL = params_sigma): the model of the target-to-neighbour
+ * VECTOR, evaluated at call time (src/point_prediction.py:115-125); c0 = covariance(i, 0, use_nugget=True) as the caller
+ * computed it (src/point_prediction.py:66).  kmax = max_c k_dev[c]; k_dev / seg_dev from pass 1. */
 int ck_local_predict(const double* xy0_dev, const double* z0_dev, ck_i64 n0, const double* xy1_dev, const double* z1_dev,
-                     ck_i64 n1, const double* xyp_dev, ck_i64 m, const double* params /*HOST*/, int n_procs, int i_pred,
-                     int metric, double max_dist, int cv, const int* k_dev, ck_i64 kmax, double* pred_dev,
-                     double* sd_dev, int* info_dev, void* ws_dev, void* stream);
+                     ck_i64 n1, const double* xyp_dev, ck_i64 m, const double* params_sigma /*HOST*/,
+                     const double* params_pred /*HOST or NULL*/, int n_procs, int i_pred, int metric, double max_dist, int cv,
+                     double c0, const int* k_dev, const int* seg_dev, ck_i64 kmax, double* pred_dev, double* sd_dev,
+                     int* info_dev, void* ws_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Multi-GPU building blocks (one process per GPU; the collectives are NCCL broadcasts issued by the host
@@ -277,10 +284,6 @@ int ck_oz_configure(int enabled, ck_i64 min_rows);
 /* 1 if ck_potrf / ck_trsm_lower hand the big updates of an n x n system to the INT8 kernel under the current switches. */
 int ck_oz_active(ck_i64 n);
 
-/* Upper bound on the CTAs (one per SM, persistent) of the following ck_oz_gemm / ck_oz_mg_update launches; 0 = all SMs.
- * Process-wide, read at enqueue time. */
-int ck_oz_set_grid(int max_ctas);
-
 /* Profiling aid: 16 clock64 stamps (thread 0) of the phases of every following diagonal-block kernel launch
  * (load, 4 x [32-column elimination, panel, trailing update], inverse assembly, store); NULL = off. */
 int ck_potf2_debug_buffer(void* dev_stamps);
@@ -303,16 +306,20 @@ int ck_oz_split(const double* src_dev, ck_i64 ld, ck_i64 rows, ck_i64 k, void* f
                 double* scales_dev, void* stream);
 
 /* C (m x n, FP64, row-major) -= A B^T from split operands: A-format slices + scales of the m-row panel,
- * B-format slices + scales of the n-row panel.  lower != 0: only entries with column <= row are updated. */
+ * B-format slices + scales of the n-row panel.  lower != 0: only entries with column <= row are updated.
+ * max_ctas > 0 caps the persistent grid (one CTA per SM) of THIS launch, so that a caller running a second stream
+ * (panel look-ahead) can leave SMs to it; 0 = every SM.  It is a launch argument, not process state: concurrent host
+ * threads / streams cannot disturb each other. */
 int ck_oz_gemm(const void* a_slices_dev, const double* a_scales_dev, ck_i64 m, const void* b_slices_dev,
-               const double* b_scales_dev, ck_i64 n, ck_i64 k, double* c_dev, ck_i64 ldc, int lower, void* stream);
+               const double* b_scales_dev, ck_i64 n, ck_i64 k, double* c_dev, ck_i64 ldc, int lower, int max_ctas,
+               void* stream);
 
 /* The same product with the masking contract of ck_mg_update: C is the local part of a 2-D block-cyclic matrix (square
  * tiles of tb elements, local tile (li, lj) = global tile (row_tile0 + li row_tile_step, col_tile0 + lj col_tile_step));
  * tiles with J > I are skipped, tiles with J == I keep their lower triangle.  m, n whole tiles. */
 int ck_oz_mg_update(const void* a_slices_dev, const double* a_scales_dev, ck_i64 m, const void* b_slices_dev,
                     const double* b_scales_dev, ck_i64 n, ck_i64 k, double* c_dev, ck_i64 ldc, ck_i64 tb, ck_i64 row_tile0,
-                    ck_i64 row_tile_step, ck_i64 col_tile0, ck_i64 col_tile_step, void* stream);
+                    ck_i64 row_tile_step, ck_i64 col_tile0, ck_i64 col_tile_step, int max_ctas, void* stream);
 
 #ifdef __cplusplus
 }

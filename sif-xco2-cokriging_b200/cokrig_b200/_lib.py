@@ -7,6 +7,8 @@ from __future__ import annotations
 
 import ctypes
 import os
+
+import torch  # noqa: F401  (first: libcokrig_b200.so links the shared CUDA runtime, which torch brings along)
 from ctypes import POINTER, c_char_p, c_double, c_int, c_int64, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -78,22 +80,21 @@ SIGNATURES = {
     "ck_oz_configure": (c_int, [c_int, c_int64]),
     "ck_potf2_debug_buffer": (c_int, [_dp]),
     "ck_oz_active": (c_int, [c_int64]),
-    "ck_oz_set_grid": (c_int, [c_int]),
     "ck_oz_debug_buffer": (c_int, [_dp]),
     "ck_oz_slices_bytes": (c_size_t, [c_int64, c_int64, c_int]),
     "ck_oz_scales_len": (c_int64, [c_int64]),
     "ck_oz_split": (c_int, [_dp, c_int64, c_int64, c_int64, _dp, _dp, _dp, c_void_p]),
     "ck_oz_mg_update": (c_int, [_dp, _dp, c_int64, _dp, _dp, c_int64, c_int64, _dp, c_int64, c_int64, c_int64, c_int64, c_int64,
-                                c_int64, c_void_p]),
-    "ck_oz_gemm": (c_int, [_dp, _dp, c_int64, _dp, _dp, c_int64, c_int64, _dp, c_int64, c_int, c_void_p]),
+                                c_int64, c_int, c_void_p]),
+    "ck_oz_gemm": (c_int, [_dp, _dp, c_int64, _dp, _dp, c_int64, c_int64, _dp, c_int64, c_int, c_int, c_void_p]),
     "ck_vario_bin_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int]),
     "ck_vario_bin": (c_int, [_dp, _dp, c_int64, c_double, _dp, _dp, c_int64, c_double, c_int, c_int, c_int,
                              c_double, _hp, c_int, _dp, _dp, _dp, c_int64, _dp, _dp, c_void_p]),
     "ck_local_predict_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "ck_local_count": (c_int, [_dp, c_int64, _dp, c_int64, _dp, c_int64, c_int, c_int, c_int, c_double, c_int,
-                               _dp, c_void_p]),
-    "ck_local_predict": (c_int, [_dp, _dp, c_int64, _dp, _dp, c_int64, _dp, c_int64, _hp, c_int, c_int, c_int,
-                                 c_double, c_int, _dp, c_int64, _dp, _dp, _dp, _dp, c_void_p]),
+                               _dp, _dp, c_void_p]),
+    "ck_local_predict": (c_int, [_dp, _dp, c_int64, _dp, _dp, c_int64, _dp, c_int64, _hp, _hp, c_int, c_int, c_int,
+                                 c_double, c_int, c_double, _dp, _dp, c_int64, _dp, _dp, _dp, _dp, c_void_p]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

@@ -182,6 +182,19 @@ class CholeskyFactor:
                                    float(c0), _ptr(pred), _ptr(var), _stream()), "ck_potrs_predict")
         return pred, var
 
+    def schur_info(self, V: torch.Tensor, cpp: torch.Tensor) -> int:
+        """Positive-definiteness of the Schur complement C_pp - V V^T (V = rows L^-1 c_j, target-major (m, n); cpp the
+        (m, m) target covariance, overwritten): 0 if PD, else the order of the first non-PD leading minor.  Together
+        with info == 0 of this factor it decides whether the reference's augmented matrix
+        [[C_pp, C_dp^T], [C_dp, Sigma]] is PD (src/joint_prediction.py:260-274) without the (m+N)^3/3 factorisation."""
+        m = V.shape[0]
+        if m == 0:
+            return 0
+        ldv = V.stride(0) if m > 1 else max(self.n, V.stride(0))
+        ldc = cpp.stride(0) if m > 1 else max(m, 1)
+        check(lib.ck_gemm_nt(_ptr(V), ldv, _ptr(V), ldv, _ptr(cpp), ldc, m, m, self.n, 1, _stream()), "ck_gemm_nt")
+        return potrf(cpp).info
+
     def logdet(self) -> torch.Tensor:
         out = torch.empty(1, dtype=F64, device=self.L.device)
         check(lib.ck_logdet(_ptr(self.L), self.n, self.ld, _ptr(out), _stream()), "ck_logdet")
@@ -323,27 +336,36 @@ def vario_bin(Xa: torch.Tensor, va: torch.Tensor, mean_a: float, Xb: torch.Tenso
 
 # ------------------------------------------------------------------------------------------------ K4
 def local_predict(coords: Sequence[torch.Tensor], values: Sequence[torch.Tensor], pcoords: torch.Tensor, params,
-                  n_procs: int, i_pred: int, metric: int, max_dist: float, cv: bool = False):
+                  n_procs: int, i_pred: int, metric: int, max_dist: float, cv: bool = False, params_pred=None,
+                  c0: Optional[float] = None):
     """Batched local-neighbourhood cokriging: returns (pred, sd, k, info) numpy arrays over targets
     (src/point_prediction.py:127-249).  info: 0 ok, >0 local matrix not PD (pred = sd = NaN),
-    -1 valid prediction but the augmented matrix is not PD (the reference only warns)."""
+    -1 valid prediction but the augmented matrix is not PD (the reference only warns).
+
+    params: the model of the local covariance matrix (the reference freezes it at construction);
+    params_pred: the model of the target-to-neighbour vector (default: params); c0: the target variance
+    the caller computed (default: sigma_i^2 + nugget_i of params_pred)."""
     dev = require_cuda()
-    _, pp = _params(params, n_procs)
+    pv, pp = _params(params, n_procs)
+    qv, qp = _params(params if params_pred is None else params_pred, n_procs)
+    if c0 is None:
+        c0 = qv[i_pred] ** 2 + qv[8 + i_pred] if n_procs == 2 else qv[0] ** 2 + qv[3]
     m = pcoords.shape[0]
     n0 = coords[0].shape[0]
     n1 = coords[1].shape[0] if n_procs == 2 else 0
     c1 = coords[1] if n_procs == 2 else None
     z1 = values[1] if n_procs == 2 else None
     k = torch.zeros(max(m, 1), dtype=torch.int32, device=dev)
+    seg = torch.zeros(8 * max(m, 1), dtype=torch.int32, device=dev)
     check(lib.ck_local_count(_ptr(coords[0]), n0, _ptr(c1), n1, _ptr(pcoords), m, n_procs, i_pred, metric,
-                             float(max_dist), int(cv), _ptr(k), _stream()), "ck_local_count")
+                             float(max_dist), int(cv), _ptr(k), _ptr(seg), _stream()), "ck_local_count")
     kmax = int(k[:m].max().item()) if m else 0
     nbytes = int(lib.ck_local_predict_workspace_bytes(m, kmax))
     ws = torch.empty(nbytes // 8 + 1, dtype=F64, device=dev)
     pred = torch.empty(max(m, 1), dtype=F64, device=dev)
     sd = torch.empty(max(m, 1), dtype=F64, device=dev)
     info = torch.zeros(max(m, 1), dtype=torch.int32, device=dev)
-    check(lib.ck_local_predict(_ptr(coords[0]), _ptr(values[0]), n0, _ptr(c1), _ptr(z1), n1, _ptr(pcoords), m, pp,
-                               n_procs, i_pred, metric, float(max_dist), int(cv), _ptr(k), kmax, _ptr(pred), _ptr(sd),
-                               _ptr(info), _ptr(ws), _stream()), "ck_local_predict")
+    check(lib.ck_local_predict(_ptr(coords[0]), _ptr(values[0]), n0, _ptr(c1), _ptr(z1), n1, _ptr(pcoords), m, pp, qp,
+                               n_procs, i_pred, metric, float(max_dist), int(cv), float(c0), _ptr(k), _ptr(seg), kmax,
+                               _ptr(pred), _ptr(sd), _ptr(info), _ptr(ws), _stream()), "ck_local_predict")
     return (pred[:m].cpu().numpy(), sd[:m].cpu().numpy(), k[:m].cpu().numpy(), info[:m].cpu().numpy())

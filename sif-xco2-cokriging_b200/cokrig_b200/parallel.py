@@ -249,18 +249,20 @@ class CudaKernels:
         st = o._stream()
         # optional split of the SMs between the panel stream and the trailing update (CK_MG_PANEL_SMS = R > 0): the
         # persistent kernel of the main stream leaves R SMs to the look-ahead work of the next tile column
+        # (a launch argument of the update: no process-wide state)
         r = int(os.environ.get("CK_MG_PANEL_SMS", str(getattr(self, "panel_sms", 0))))
+        cap = 0
         if r > 0:
             nsm = torch.cuda.get_device_properties(self.device).multi_processor_count
             on_panel = torch.cuda.current_stream(self.device) == self.panel
-            self.lib.ck_oz_set_grid(r if on_panel else max(nsm - r, 1))
+            cap = r if on_panel else max(nsm - r, 1)
         self.check(self.lib.ck_oz_split(o._ptr(A), A.stride(0), m, k, o._ptr(fa), None, o._ptr(sa), st), "ck_oz_split")
         self.check(self.lib.ck_oz_split(o._ptr(B), B.stride(0), n, k, None, o._ptr(fb), o._ptr(sb), st), "ck_oz_split")
         if tb:
             self.check(self.lib.ck_oz_mg_update(o._ptr(fa), o._ptr(sa), m, o._ptr(fb), o._ptr(sb), n, k, o._ptr(C), C.stride(0),
-                                                tb, gi0, gis, gj0, gjs, st), "ck_oz_mg_update")
+                                                tb, gi0, gis, gj0, gjs, cap, st), "ck_oz_mg_update")
         else:
-            self.check(self.lib.ck_oz_gemm(o._ptr(fa), o._ptr(sa), m, o._ptr(fb), o._ptr(sb), n, k, o._ptr(C), C.stride(0), 0, st),
+            self.check(self.lib.ck_oz_gemm(o._ptr(fa), o._ptr(sa), m, o._ptr(fb), o._ptr(sb), n, k, o._ptr(C), C.stride(0), 0, cap, st),
                        "ck_oz_gemm")
 
     def trsm(self, pack: torch.Tensor, tb: int, rows: torch.Tensor, out: torch.Tensor) -> None:

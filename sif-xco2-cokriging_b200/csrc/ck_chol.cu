@@ -266,13 +266,10 @@ static int gemm_launch(const GemmArgs& g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return CK_OK;
   const bool vec = ((((uintptr_t)g.A | (uintptr_t)g.B | (uintptr_t)g.C) & 15) == 0) && !((g.lda | g.ldb | g.ldc) & 1);
   const bool kfull = vec && (g.K % G_BK == 0);
-  static bool attr_done = false;
-  if (!attr_done) {
-    CK_CUDA(cudaFuncSetAttribute(ck_gemm_nt_kernel<WM, WN, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-    CK_CUDA(cudaFuncSetAttribute(ck_gemm_nt_kernel<WM, WN, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-    CK_CUDA(cudaFuncSetAttribute(ck_gemm_nt_kernel<WM, WN, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-    attr_done = true;
-  }
+  static CkPerDevice attr_a, attr_b, attr_c;  // one set per <WM, WN> instantiation
+  CK_SET_SMEM_ONCE(attr_a, (ck_gemm_nt_kernel<WM, WN, true, true>), SMEM);
+  CK_SET_SMEM_ONCE(attr_b, (ck_gemm_nt_kernel<WM, WN, true, false>), SMEM);
+  CK_SET_SMEM_ONCE(attr_c, (ck_gemm_nt_kernel<WM, WN, false, false>), SMEM);
   const long long tm = (g.M + BM - 1) / BM, tn = (g.N + BN - 1) / BN;
   dim3 grid;
   if (g.lower_only == 1) {
@@ -690,11 +687,8 @@ extern "C" int ck_potf2_debug_buffer(void* dev_stamps) {
 
 static int potf2_launch(double* a, long long ld, int nb, double* x, int* info, int k0, cudaStream_t st) {
   constexpr size_t SMEM = P_SMEM_DOUBLES * sizeof(double);
-  static bool attr_done = false;
-  if (!attr_done) {
-    CK_CUDA(cudaFuncSetAttribute(ck_potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-    attr_done = true;
-  }
+  static CkPerDevice attr;
+  CK_SET_SMEM_ONCE(attr, ck_potf2_inv_kernel, SMEM);
   ck_potf2_inv_kernel<<<1, P_THREADS, SMEM, st>>>(a, ld, nb, x, info, k0, g_potf2_dbg);
   CK_LAUNCH_CHECK();
   return CK_OK;
@@ -848,7 +842,7 @@ extern "C" int ck_potrf(double* a, ck_i64 n, ck_i64 ld, void* ws, int* info, voi
       }
       if (la_now) {
         // (a) columns of the next aggregate: A[k1:, k1:k2] -= P P[k1:k2]^T  (every SM)
-        if ((rc = ck_oz_gemm(z.fa, z.sa, rows, z.fb, z.sa, off, kk, a + k1 * ld + k1, ld, 1, stream))) return rc;
+        if ((rc = ck_oz_gemm(z.fa, z.sa, rows, z.fb, z.sa, off, kk, a + k1 * ld + k1, ld, 1, 0, stream))) return rc;
         CK_CUDA(cudaEventRecord(oside->ev_a, st));
         CK_CUDA(cudaStreamWaitEvent(oside->s, oside->ev_a, 0));
         if ((rc = factor_range(ocs, b1, b2))) return rc;  // panel chain of the next aggregate, beside (b)
@@ -856,14 +850,13 @@ extern "C" int ck_potrf(double* a, ck_i64 n, ck_i64 ld, void* ws, int* info, voi
         // (b) the rest: A[k2:, k2:] -= P[k2:] P[k2:]^T on all but `la` SMs
         const char* fa2 = static_cast<const char*>(z.fa) + (size_t)(off / 128) * ck_oz_slices_bytes(128, kk, 0);
         const char* fb2 = static_cast<const char*>(z.fb) + (size_t)(off / 64) * ck_oz_slices_bytes(64, kk, 1);
-        const int old_cap = ck_oz_grid_swap(ck_oz_num_sms() - la);
-        rc = ck_oz_gemm(fa2, z.sa + off, rows - off, fb2, z.sa + off, rows - off, kk, a + k2 * ld + k2, ld, 1, stream);
-        ck_oz_grid_swap(old_cap);
-        if (rc) return rc;
+        if ((rc = ck_oz_gemm(fa2, z.sa + off, rows - off, fb2, z.sa + off, rows - off, kk, a + k2 * ld + k2, ld, 1,
+                             ck_oz_num_sms() - la, stream)))
+          return rc;
         CK_CUDA(cudaStreamWaitEvent(st, oside->ev_c, 0));
       } else {
         if (use_oz) {
-          if ((rc = ck_oz_gemm(z.fa, z.sa, rows, z.fb, z.sa, rows, kk, a + k1 * ld + k1, ld, 1, stream))) return rc;
+          if ((rc = ck_oz_gemm(z.fa, z.sa, rows, z.fb, z.sa, rows, kk, a + k1 * ld + k1, ld, 1, 0, stream))) return rc;
         } else {
           GemmArgs u;  // A[k1:, k1:] -= P P^T, P = A[k1:, k0:k1], lower tiles
           u.A = a + k1 * ld + k0; u.lda = ld;
@@ -971,14 +964,8 @@ static int trsv_update_launch(const double* lpan, ck_i64 ld, ck_i64 rows, ck_i64
   const size_t smem = (size_t)nrhs * kk * sizeof(double);  // <= 8 x 1024 x 8 B = 64 KB
 #define CK_TRSV(NR)                                                                                                    \
   case NR: {                                                                                                           \
-    static bool attr_done[64] = {};                                                                                    \
-    int dev = 0;                                                                                                       \
-    CK_CUDA(cudaGetDevice(&dev));                                                                                      \
-    if (dev < 0 || dev >= 64 || !attr_done[dev]) {                                                                     \
-      CK_CUDA(cudaFuncSetAttribute(ck_trsv_update_kernel<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize,             \
-                                   NR * 1024 * (int)sizeof(double)));                                                  \
-      if (dev >= 0 && dev < 64) attr_done[dev] = true;                                                                 \
-    }                                                                                                                  \
+    static CkPerDevice attr;                                                                                           \
+    CK_SET_SMEM_ONCE(attr, ck_trsv_update_kernel<NR>, NR * 1024 * sizeof(double));                                     \
     ck_trsv_update_kernel<NR><<<(unsigned)blocks, 256, smem, st>>>(lpan, ld, rows, (int)kk, rhs, ld_rhs, k0, k1, vec); \
   } break;
   switch ((int)nrhs) {
@@ -1075,21 +1062,20 @@ extern "C" int ck_trsm_lower(const double* l, ck_i64 n, ck_i64 ld, const void* w
       }
       if (la_now) {
         // (a) columns of the next aggregate: R[:, k1:k2] -= V L[k1:k2]^T  (every SM)
-        if ((rc = ck_oz_gemm(z.fa, z.sa, nrhs, z.fb, z.sb, off, kk, rhs + k1, ld_rhs, 0, stream))) return rc;
+        if ((rc = ck_oz_gemm(z.fa, z.sa, nrhs, z.fb, z.sb, off, kk, rhs + k1, ld_rhs, 0, 0, stream))) return rc;
         CK_CUDA(cudaEventRecord(oside->ev_a, st));
         CK_CUDA(cudaStreamWaitEvent(oside->s, oside->ev_a, 0));
         if ((rc = solve_range(ocs, b1, b2))) return rc;  // small solves of the next aggregate, beside (b)
         CK_CUDA(cudaEventRecord(oside->ev_c, oside->s));
         // (b) the rest: R[:, k2:] -= V L[k2:]^T on all but `la` SMs
         const char* fb2 = static_cast<const char*>(z.fb) + (size_t)(off / 64) * ck_oz_slices_bytes(64, kk, 1);
-        const int old_cap = ck_oz_grid_swap(ck_oz_num_sms() - la);
-        rc = ck_oz_gemm(z.fa, z.sa, nrhs, fb2, z.sb + off, cols - off, kk, rhs + k2, ld_rhs, 0, stream);
-        ck_oz_grid_swap(old_cap);
-        if (rc) return rc;
+        if ((rc = ck_oz_gemm(z.fa, z.sa, nrhs, fb2, z.sb + off, cols - off, kk, rhs + k2, ld_rhs, 0, ck_oz_num_sms() - la,
+                             stream)))
+          return rc;
         CK_CUDA(cudaStreamWaitEvent(st, oside->ev_c, 0));
       } else {
         if (use_oz) {
-          if ((rc = ck_oz_gemm(z.fa, z.sa, nrhs, z.fb, z.sb, cols, kk, rhs + k1, ld_rhs, 0, stream))) return rc;
+          if ((rc = ck_oz_gemm(z.fa, z.sa, nrhs, z.fb, z.sb, cols, kk, rhs + k1, ld_rhs, 0, 0, stream))) return rc;
         } else {
           GemmArgs r;  // R[:, k1:] -= V[:, k0:k1] L[k1:, k0:k1]^T
           r.A = rhs + k0; r.lda = ld_rhs;

@@ -54,8 +54,22 @@ int ck_block_matern(const CkParams& p, int i, int j, int use_nugget, CkMatern* o
 int ck_block_launch(const double* xy1, ck_i64 n1, const double* xy2, ck_i64 n2, int metric, const CkMatern& P, int value,
                     double* out, ck_i64 ld, double* out_t, ck_i64 ld_t, int symmetric, cudaStream_t st);
 
-// INT8 update kernel (ck_ozaki.cu): CTA cap of the following launches (returns the previous cap; 0 = every SM), SM count
-int ck_oz_grid_swap(int max_ctas);
+// INT8 update kernel (ck_ozaki.cu): SM count of the current device
 int ck_oz_num_sms();
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE attribute: every launcher keeps one flag per device
+// (a process may drive several GPUs) and sets the attribute the first time it launches on each of them.
+struct CkPerDevice {
+  bool done[64] = {};
+};
+#define CK_SET_SMEM_ONCE(flags, kernel, bytes)                                                                  \
+  do {                                                                                                          \
+    int dev_ = 0;                                                                                               \
+    CK_CUDA(cudaGetDevice(&dev_));                                                                              \
+    if (dev_ < 0 || dev_ >= 64 || !(flags).done[dev_]) {                                                        \
+      CK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));         \
+      if (dev_ >= 0 && dev_ < 64) (flags).done[dev_] = true;                                                    \
+    }                                                                                                           \
+  } while (0)
 
 static inline cudaStream_t ck_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }

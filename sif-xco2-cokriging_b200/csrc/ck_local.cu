@@ -1,233 +1,456 @@
 // ck_local.cu -- K4: batched local-neighbourhood (point) cokriging for sm_100a.
 //
-// One CTA per prediction target (persistent over targets, one workspace slot per CTA):
-//   1. ordered compaction of the data within max_dist (process 0 then 1, index order -- the order of
-//      the reference's boolean masks, src/point_prediction.py:127-151);
-//   2. the local covariance matrix is RE-COMPUTED from coordinates (cheaper than gathering k^2
-//      entries of a stored N x N Sigma and needs no N^2 memory), lower triangle only, with two
-//      extra rows appended: c (target-to-neighbour covariances) and z (neighbour data);
-//   3. right-looking blocked Cholesky (panel 32) applied to the (k+2) x k array: the panel step
-//      that turns rows of S into rows of L turns the two extra rows into v = L^{-1} c, y = L^{-1} z,
-//      so no separate triangular solve is needed;
-//   4. pred = v . y,  sd = sqrt(max(c0 - v . v, 0))   (src/point_prediction.py:200-222).
+// Replaces the reference's per-target Python loop (src/point_prediction.py:127-249: boolean neighbour masks, np.ix_
+// gathers from the stored Sigma blocks, two k x k Cholesky factorisations per target) by two launches for ALL targets:
+//
+//   ck_local_count_kernel    neighbour counts per target, split into the eight (process, scan segment) pieces that the
+//                            second kernel needs to compact the neighbours IN THE REFERENCE'S ORDER (process 0 then 1,
+//                            index order = the order of the boolean masks) without re-counting;
+//   ck_local_predict_kernel  persistent CTAs of 128 threads (up to 4 per SM, one target each, targets handed out by an
+//                            atomic counter):
+//     1. scan + ordered compaction.  A conservative bounding test (|dx|, |dy| for Euclid; latitude band and a
+//        longitude bound for haversine, margins 1e-12 / 1e-9 >> the rounding of the distance) rejects most data with
+//        a handful of instructions; survivors get the reference-order distance (bit-identical Euclid, libm-level
+//        haversine), so the neighbour sets equal the reference's.  The kept points, their covariance with the target
+//        (c) and their data (z) go to shared memory.
+//     2. LEFT-looking blocked Cholesky in 32-column block columns on the (kp + 2)-row array  [Sigma_loc ; c^T ; z^T]
+//        (kp = k rounded up to 32, identity padded).  For block column J and a 64-row tile:
+//            W = Sigma[tile, J] - L[tile, 0:J) L[J, 0:J)^T
+//        The Sigma entries are RE-COMPUTED from the coordinates straight into the FP64 DMMA accumulator registers
+//        (no k x k matrix is ever stored or gathered: the only array in memory is L itself, written once), the
+//        product is FP64 tensor-core DMMA (mma.sync m8n8k4) fed by a cp.async-staged pipeline from the L2-resident
+//        workspace slot of the CTA.  The 32 x 32 diagonal block is eliminated by one warp with register-resident
+//        rows and shuffles (pivot reciprocal by Newton, square roots off the chain), its inverse X_d formed by
+//        forward substitution, and the rows below become  P = W X_d^T  (DMMA again, skipping the zero half of X_d).
+//        Because c and z ride along as two extra rows, the sweep leaves v = L^-1 c and y = L^-1 z: no separate solve.
+//     3. pred = v . y,  sd = sqrt(max(c0 - v . v, 0))   (src/point_prediction.py:200-222); NaN for an empty or
+//        non-positive-definite neighbourhood like the reference.
+//   While one CTA sits in its latency-bound 32-column elimination the other CTAs of the SM keep the FP64 pipe busy.
+//
+// Matern evaluation: when the three blocks of the joint model share one closed-form order nu in {1/2, 3/2, 5/2, 7/2}
+// (every BASELINE config) the matrix entries use the branch-free polynomial path of K1 (<= 2 ulp per piece,
+// ck_math.cuh); otherwise the reference-order generic path (K_nu).  The target-to-neighbour vector c always uses the
+// reference-order path on the exact selection distances.
 #include "ck_common.cuh"
 
-constexpr int LW = 32;         // panel width
-constexpr int LT = 64;         // trailing-update tile
-constexpr int L_THREADS = 256;
+constexpr int LP = 32;             // block-column (panel) width
+constexpr int LTM = 64;            // rows per tile
+constexpr int LK = 16;             // k-depth per pipeline stage
+constexpr int LLD = LK + 4;        // staging row stride (doubles): % 16 == 4 -> conflict-free DMMA fragment loads
+constexpr int LSTG = 2;            // pipeline stages
+constexpr int LWLD = LP + 4;       // row stride of the W tile and of X_d
+constexpr int L_THREADS = 128;
+constexpr int L_WARPS = L_THREADS / 32;
+constexpr int L_STAGE_ELEMS = (LTM + LP) * LLD;
+constexpr int L_SMEM_KMAX = 2048;  // neighbour records live in shared memory up to this k, in the workspace beyond
+constexpr int L_FAST_NONE = -1;
+static_assert(LTM * LWLD <= LSTG * L_STAGE_ELEMS, "the W tile aliases the staging buffers");
 
 struct LocalArgs {
   const double* xy[2]; const double* z[2]; long long n[2];
   const double* xyp; long long m;
-  CkMatern S[2][2];  // joint-model blocks (S[1][0] == S[0][1])
-  CkMatern C[2];     // target-to-process-j blocks for the predicted process (own block carries the nugget)
+  CkMatern S[3];    // joint-model blocks 00, 01, 11 (frozen at Predictor construction, src/point_prediction.py:42)
+  CkMatern C[2];    // target-to-process-j blocks for the predicted process (own block carries the nugget)
   int n_procs, i_pred, metric, cv;
   double max_dist, c0;
-  const int* kcount; long long kmax, ldk;
+  const int* kcount; const int* kseg; long long kmax, kmaxp;
   double* pred; double* sd; int* info;
-  double* ws_mat;   // slots x (kmax+2) x ldk
-  double* ws_pts;   // slots x kmax x 4   (CkPoint a, b, c + process id)
+  double* ws;       // slots x [(kmaxp + 2) x kmaxp factor rows | optional neighbour records]
+  long long slot_stride;
+  int pts_in_ws;
+  unsigned int* counter;
 };
 
 // out-of-line so that the five Matern variants are instantiated once per kernel, not per call site
 static __device__ __noinline__ double cov_dyn(const CkMatern& P, double h) { return ck_matern_cov_dyn(P, h); }
 
+__device__ __forceinline__ void l_cp_async16(unsigned dst, const void* src, unsigned on) {
+  asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %2, 0;\n @p cp.async.cg.shared.global [%0], [%1], 16;\n}\n" ::"r"(dst), "l"(src),
+               "r"(on));
+}
+__device__ __forceinline__ void l_cp_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void l_cp_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+__device__ __forceinline__ void l_dmma(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// ------------------------------------------------------------------------------------------------
+// neighbour scan
+// ------------------------------------------------------------------------------------------------
+// per-target constants of the conservative pre-filter
+struct LocalFilter {
+  double p0, p1;     // raw target coordinates
+  double lim0;       // Euclid: max_dist (1 + 1e-12);  haversine: latitude band in degrees (or inf)
+  double lon_k;      // haversine: reject when |x_red| * lon_k > 1  (0: longitude test off)
+};
+
 template <int METRIC>
+__device__ __forceinline__ LocalFilter local_filter(const LocalArgs& g, double p0, double p1) {
+  LocalFilter f;
+  f.p0 = p0; f.p1 = p1;
+  const double inf = __longlong_as_double(0x7FF0000000000000LL);
+  if (METRIC == CK_METRIC_EUCLID) {
+    f.lim0 = g.max_dist * (1.0 + 1.0e-12);
+    f.lon_k = 0.0;
+  } else {
+    // haversine >= R |dlat| and >= 2 R asin(sqrt(cos(lat1) cos(lat2)) |sin(dlon / 2)|); |sin x| >= (2 / pi) |x| on
+    // [-pi/2, pi/2].  Margins 1e-9 relative (the computed distance is good to ~1e-15).
+    const double md = g.max_dist * (1.0 + 1.0e-9);
+    const double delta = md / CK_EARTH_RADIUS;  // radians
+    const bool lat_ok = fabs(p0) <= 90.0 && md >= 0.0;
+    f.lim0 = lat_ok ? delta / CK_DEG2RAD : inf;
+    f.lon_k = 0.0;
+    const double phi = fabs(p0) * CK_DEG2RAD + delta;
+    if (lat_ok && 0.5 * delta < 1.5707963267948966 && phi < 1.5707963267948966) {
+      const double cmin = sqrt(cos(p0 * CK_DEG2RAD) * cos(phi));
+      const double smax = sin(0.5 * delta) * (1.0 + 1.0e-9);
+      if (cmin > 0.0 && smax > 0.0) f.lon_k = 0.6366197723675814 * cmin / smax;  // (2 / pi) cmin / smax
+    }
+  }
+  return f;
+}
+
+// true: the datum cannot be within max_dist (decided without the exact distance)
+template <int METRIC>
+__device__ __forceinline__ bool local_reject(const LocalFilter& f, double q0, double q1) {
+  if (METRIC == CK_METRIC_EUCLID) return fabs(q0 - f.p0) > f.lim0 || fabs(q1 - f.p1) > f.lim0;
+  if (fabs(q0 - f.p0) > f.lim0 && fabs(q0) <= 90.0) return true;
+  if (f.lon_k > 0.0 && fabs(q0) <= 90.0) {
+    const double x = 0.5 * CK_DEG2RAD * (q1 - f.p1);
+    const double xr = x - 3.141592653589793 * rint(x * 0.3183098861837907);
+    return fabs(xr) * f.lon_k > 1.0;
+  }
+  return false;
+}
+
 __device__ __forceinline__ bool local_keep(const LocalArgs& g, int proc, double d) {
   if (!(d <= g.max_dist)) return false;
   if (g.cv && proc == g.i_pred && !(d > 0.0)) return false;
   return true;
 }
 
-template <int METRIC>
-__global__ void __launch_bounds__(L_THREADS) ck_local_count_kernel(LocalArgs g, int* __restrict__ kout) {
-  __shared__ int red[L_THREADS];
-  for (long long c = blockIdx.x; c < g.m; c += gridDim.x) {
-    const CkPoint p0 = ck_prepare_point(METRIC, g.xyp[2 * c], g.xyp[2 * c + 1]);
-    int cnt = 0;
-    for (int proc = 0; proc < g.n_procs; ++proc)
-      for (long long i = threadIdx.x; i < g.n[proc]; i += L_THREADS) {
-        const CkPoint q = ck_prepare_point(METRIC, g.xy[proc][2 * i], g.xy[proc][2 * i + 1]);
-        cnt += local_keep<METRIC>(g, proc, ck_dist<METRIC>(p0, q)) ? 1 : 0;
+__device__ __forceinline__ long long local_seglen(long long n) { return ((n + L_WARPS - 1) / L_WARPS + 31) / 32 * 32; }
+
+// One warp scans its segment of process `proc` in index order.  STORE: kept points are appended at `off` (warp-private,
+// ordered); returns the number kept.
+template <int METRIC, bool STORE>
+__device__ __forceinline__ int local_scan_segment(const LocalArgs& g, const LocalFilter& f, const CkPoint& p0, int proc, int warp,
+                                                  int lane, int off, double* pa, double* pb, double* pc, double* pcv, double* pzv) {
+  const long long n = g.n[proc], sl = local_seglen(n);
+  const long long b0 = (long long)warp * sl, b1 = (b0 + sl < n) ? b0 + sl : n;
+  const double* xy = g.xy[proc];
+  int cnt = 0;
+  for (long long base = b0; base < b1; base += 32) {
+    const long long i = base + lane;
+    bool keep = false;
+    double d = 0.0;
+    CkPoint q;
+    q.a = q.b = q.c = 0.0;
+    if (i < b1) {
+      const double2 v = *reinterpret_cast<const double2*>(xy + 2 * i);
+      if (!local_reject<METRIC>(f, v.x, v.y)) {
+        q = ck_prepare_point(METRIC, v.x, v.y);
+        d = ck_dist<METRIC>(p0, q);
+        keep = local_keep(g, proc, d);
       }
-    red[threadIdx.x] = cnt;
-    __syncthreads();
-    for (int h = L_THREADS / 2; h > 0; h >>= 1) {
-      if ((int)threadIdx.x < h) red[threadIdx.x] += red[threadIdx.x + h];
-      __syncthreads();
     }
-    if (threadIdx.x == 0) kout[c] = red[0];
+    const unsigned mask = __ballot_sync(0xffffffffu, keep);
+    if (STORE && keep) {
+      const int pos = off + cnt + __popc(mask & ((1u << lane) - 1u));
+      pa[pos] = q.a;
+      pb[pos] = q.b;
+      if (METRIC == CK_METRIC_HAVERSINE) pc[pos] = q.c;
+      pcv[pos] = cov_dyn(g.C[proc], d);
+      pzv[pos] = g.z[proc][i];
+    }
+    cnt += __popc(mask);
+  }
+  return cnt;
+}
+
+template <int METRIC>
+__global__ void __launch_bounds__(L_THREADS) ck_local_count_kernel(const __grid_constant__ LocalArgs g, int* __restrict__ kout, int* __restrict__ kseg) {
+  __shared__ int seg[2 * L_WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (long long c = blockIdx.x; c < g.m; c += gridDim.x) {
+    const double t0 = g.xyp[2 * c], t1 = g.xyp[2 * c + 1];
+    const CkPoint p0 = ck_prepare_point(METRIC, t0, t1);
+    const LocalFilter f = local_filter<METRIC>(g, t0, t1);
+    for (int proc = 0; proc < 2; ++proc) {
+      int cnt = 0;
+      if (proc < g.n_procs)
+        cnt = local_scan_segment<METRIC, false>(g, f, p0, proc, warp, lane, 0, nullptr, nullptr, nullptr, nullptr, nullptr);
+      if (lane == 0) seg[proc * L_WARPS + warp] = cnt;
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * L_WARPS) kseg[c * (2 * L_WARPS) + threadIdx.x] = seg[threadIdx.x];
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int s = 0; s < 2 * L_WARPS; ++s) tot += seg[s];
+      kout[c] = tot;
+    }
     __syncthreads();
   }
 }
 
-template <int METRIC>
-__global__ void __launch_bounds__(L_THREADS) ck_local_predict_kernel(LocalArgs g) {
-  __shared__ double Ds[LW][LW + 1];
-  __shared__ double Pa[LT][LW + 1], Pb[LT][LW + 1];
-  __shared__ int wcount[L_THREADS / 32];
-  __shared__ int s_total, s_fail;
-  __shared__ double red[L_THREADS];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  double* M = g.ws_mat + (size_t)blockIdx.x * (size_t)(g.kmax + 2) * (size_t)g.ldk;
-  double* pts = g.ws_pts + (size_t)blockIdx.x * (size_t)g.kmax * 4;
-  const long long ld = g.ldk;
-  const double qnan = __longlong_as_double(0x7FF8000000000000LL);
+// ------------------------------------------------------------------------------------------------
+// factor + solve
+// ------------------------------------------------------------------------------------------------
+// Entry (i, j) of the block [Sigma_loc ; c ; z] padded with the identity to kp (i >= j inside the matrix part).
+template <int METRIC, int FAST>
+__device__ __forceinline__ double local_cov_entry(const LocalArgs& g, int i, int j, int k0, const double* pa, const double* pb,
+                                                  const double* pc) {
+  CkPoint pi, pj;
+  pi.a = pa[i]; pi.b = pb[i];
+  pj.a = pa[j]; pj.b = pb[j];
+  pi.c = pj.c = 0.0;
+  if (METRIC == CK_METRIC_HAVERSINE) { pi.c = pc[i]; pj.c = pc[j]; }
+  // j <= i and process 0 comes first: (proc_j, proc_i) in {(0,0), (0,1), (1,1)}; rows of the reference block come from
+  // the lower process id (src/point_prediction.py:159-179)
+  const int blk = (i < k0) ? 0 : (j < k0 ? 1 : 2);
+  if (FAST != L_FAST_NONE) return ck_matern_cov_fast<FAST>(g.S[blk], ck_dist_fast<METRIC>(pj, pi));
+  return cov_dyn(g.S[blk], ck_dist<METRIC>(pj, pi));
+}
 
-  for (long long c = blockIdx.x; c < g.m; c += gridDim.x) {
+template <int METRIC, int FAST>
+__device__ __forceinline__ double local_entry(const LocalArgs& g, int i, int j, int k, int kp, int k0, const double* pa,
+                                              const double* pb, const double* pc, const double* pcv, const double* pzv) {
+  if (i < kp) {
+    if (j > i) return 0.0;
+    if (i >= k) return (i == j) ? 1.0 : 0.0;
+    return local_cov_entry<METRIC, FAST>(g, i, j, k0, pa, pb, pc);
+  }
+  if (j >= k) return 0.0;
+  return (i == kp) ? pcv[j] : ((i == kp + 1) ? pzv[j] : 0.0);
+}
+
+template <int METRIC, int FAST>
+__global__ void __launch_bounds__(L_THREADS, 4) ck_local_predict_kernel(const __grid_constant__ LocalArgs g) {
+  extern __shared__ __align__(16) double lsm[];
+  double* stage = lsm;                                  // LSTG x (LTM + LP) x LLD; aliased by the W tile
+  double* Wt = lsm;                                     // LTM x LWLD
+  double* Xd = stage + LSTG * L_STAGE_ELEMS;            // LP x LWLD: (L_d^-1)[r][c]
+  double* rsd = Xd + LP * LWLD;                         // 1 / L_d[k][k]
+  double* red = rsd + LP;                               // L_THREADS
+  double* pts_sm = red + L_THREADS;
+  __shared__ int s_next, s_fail;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g4 = lane >> 2, t4 = lane & 3;
+  double* Lw = g.ws + (size_t)blockIdx.x * (size_t)g.slot_stride;
+  const long long ld = g.kmaxp;
+  const long long kcap = (g.kmax + 7) / 8 * 8;
+  double* pbase = g.pts_in_ws ? Lw + (size_t)(g.kmaxp + 2) * (size_t)g.kmaxp : pts_sm;
+  double *pa = pbase, *pb = pa + kcap, *pcv = pb + kcap, *pzv = pcv + kcap, *pc = pzv + kcap;
+  const double qnan = __longlong_as_double(0x7FF8000000000000LL);
+  const unsigned sbase = (unsigned)__cvta_generic_to_shared(stage);
+
+  for (;;) {
+    if (tid == 0) { s_next = (int)atomicAdd(g.counter, 1u); s_fail = 0; }
+    __syncthreads();
+    const long long c = s_next;
+    __syncthreads();
+    if (c >= g.m) break;
     const int k = g.kcount[c];
     if (k <= 0) {
       if (tid == 0) { g.pred[c] = qnan; g.sd[c] = qnan; g.info[c] = 0; }
       continue;
     }
-    const CkPoint p0 = ck_prepare_point(METRIC, g.xyp[2 * c], g.xyp[2 * c + 1]);
-    // ---- 1. ordered compaction; also fills row k (c vector) and row k+1 (z) ----
-    if (tid == 0) { s_total = 0; s_fail = 0; }
-    __syncthreads();
-    for (int proc = 0; proc < g.n_procs; ++proc) {
-      for (long long base = 0; base < g.n[proc]; base += L_THREADS) {
-        const long long i = base + tid;
-        bool keep = false;
-        CkPoint q;
-        double d = 0.0;
-        if (i < g.n[proc]) {
-          q = ck_prepare_point(METRIC, g.xy[proc][2 * i], g.xy[proc][2 * i + 1]);
-          d = ck_dist<METRIC>(p0, q);
-          keep = local_keep<METRIC>(g, proc, d);
-        }
-        const unsigned mask = __ballot_sync(0xffffffffu, keep);
-        if (lane == 0) wcount[warp] = __popc(mask);
-        __syncthreads();
-        int off = s_total;
-        for (int w = 0; w < warp; ++w) off += wcount[w];
-        if (keep) {
-          const int pos = off + __popc(mask & ((1u << lane) - 1u));
-          if (pos < k) {
-            pts[4 * pos + 0] = q.a; pts[4 * pos + 1] = q.b; pts[4 * pos + 2] = q.c; pts[4 * pos + 3] = (double)proc;
-            M[(long long)k * ld + pos] = cov_dyn(g.C[proc], d);
-            M[(long long)(k + 1) * ld + pos] = g.z[proc][i];
-          }
-        }
-        __syncthreads();
-        if (tid == 0) {
-          int tot = 0;
-          for (int w = 0; w < L_THREADS / 32; ++w) tot += wcount[w];
-          s_total += tot;
-        }
-        __syncthreads();
+    // ---- 1. scan + ordered compaction (offsets from the eight segment counts of the first pass)
+    int k0 = 0;
+    {
+      const int* sg = g.kseg + c * (2 * L_WARPS);
+      int off0 = 0, off1 = 0;
+      for (int w = 0; w < L_WARPS; ++w) {
+        const int s0 = sg[w], s1 = sg[L_WARPS + w];
+        if (w < warp) { off0 += s0; off1 += s1; }
+        k0 += s0;
       }
-    }
-    // ---- 2. lower triangle of the local covariance ----
-    for (int a = warp; a < k; a += L_THREADS / 32) {
-      CkPoint pa; pa.a = pts[4 * a]; pa.b = pts[4 * a + 1]; pa.c = pts[4 * a + 2];
-      const int proca = (int)pts[4 * a + 3];
-      for (int b = lane; b <= a; b += 32) {
-        CkPoint pb; pb.a = pts[4 * b]; pb.b = pts[4 * b + 1]; pb.c = pts[4 * b + 2];
-        const int procb = (int)pts[4 * b + 3];
-        // distance argument order follows the reference block (i <= j): rows from the lower process id
-        const double d = (procb <= proca) ? ck_dist<METRIC>(pb, pa) : ck_dist<METRIC>(pa, pb);
-        M[(long long)a * ld + b] = cov_dyn(g.S[procb][proca], d);
-      }
+      const double t0 = g.xyp[2 * c], t1 = g.xyp[2 * c + 1];
+      const CkPoint p0 = ck_prepare_point(METRIC, t0, t1);
+      const LocalFilter f = local_filter<METRIC>(g, t0, t1);
+      local_scan_segment<METRIC, true>(g, f, p0, 0, warp, lane, off0, pa, pb, pc, pcv, pzv);
+      if (g.n_procs == 2) local_scan_segment<METRIC, true>(g, f, p0, 1, warp, lane, k0 + off1, pa, pb, pc, pcv, pzv);
     }
     __syncthreads();
-    // ---- 3. blocked Cholesky on the (k+2) x k array ----
-    const int R = k + 2;
-    for (int j0 = 0; j0 < k; j0 += LW) {
-      const int w = (k - j0 < LW) ? k - j0 : LW;
-      for (int e = tid; e < LW * LW; e += L_THREADS) {
-        const int i = e / LW, cc = e % LW;
-        double v = (i == cc) ? 1.0 : 0.0;
-        if (i < w && cc < w && cc <= i) v = M[(long long)(j0 + i) * ld + j0 + cc];
-        else if (i < w && cc < w) v = 0.0;
-        Ds[i][cc] = v;
-      }
-      __syncthreads();
-      if (warp == 0) {  // unblocked factorisation of the diagonal block, lane = row
-        for (int jj = 0; jj < LW; ++jj) {
-          const double dj = Ds[jj][jj];
-          if (!(dj > 0.0) && lane == 0 && s_fail == 0) s_fail = j0 + jj + 1;
-          const double sq = sqrt(dj);
-          __syncwarp();
-          if (lane == jj) Ds[jj][jj] = sq;
-          if (lane > jj) Ds[lane][jj] = Ds[lane][jj] / sq;
-          __syncwarp();
-          if (lane > jj) {
-            const double l = Ds[lane][jj];
-            for (int cc = jj + 1; cc <= lane; ++cc) Ds[lane][cc] -= l * Ds[cc][jj];
+
+    // ---- 2. left-looking blocked Cholesky of [Sigma_loc ; c ; z]
+    const int kp = (k + LP - 1) / LP * LP, R = kp + 2;
+    for (int c0 = 0; c0 < kp; c0 += LP) {
+      const int ntile = (R - c0 + LTM - 1) / LTM;
+      const int KT = c0 / LK;
+      for (int t = 0; t < ntile; ++t) {
+        const int i0 = c0 + t * LTM;
+        const int wrow = i0 + 16 * warp;  // first row of this warp's 16 x 32 piece
+        __syncthreads();                  // the previous tile's W (aliasing the staging buffers) has been consumed
+        // operand loader: A = L[i0 : i0 + 64, 0 : c0), B = L[c0 : c0 + 32, 0 : c0); per stage 96 rows x 8 chunks of 16 B
+        auto load_stage = [&](int s, int kt) {
+          const unsigned dst0 = sbase + (unsigned)(s * L_STAGE_ELEMS * 8);
+#pragma unroll
+          for (int it = 0; it < (LTM + LP) * (LK / 2) / L_THREADS; ++it) {
+            const int idx = tid + it * L_THREADS, row = idx >> 3, ch = idx & 7;
+            const int grow = row < LTM ? i0 + row : c0 + (row - LTM);
+            const unsigned on = (kt < KT && grow < R) ? 1u : 0u;
+            l_cp_async16(dst0 + (unsigned)((row * LLD + ch * 2) * 8), Lw + (long long)(on ? grow : 0) * ld + kt * LK + ch * 2, on);
           }
-          __syncwarp();
+        };
+        if (KT > 0) {
+#pragma unroll
+          for (int s = 0; s < LSTG - 1; ++s) {
+            load_stage(s, s);
+            l_cp_commit();
+          }
         }
-      }
-      __syncthreads();
-      for (int e = tid; e < w * w; e += L_THREADS) {
-        const int i = e / w, cc = e % w;
-        if (cc <= i) M[(long long)(j0 + i) * ld + j0 + cc] = Ds[i][cc];
-      }
-      // panel: rows below the diagonal block (incl. the two extra rows): row <- row L_d^{-T}
-      for (int i = j0 + w + tid; i < R; i += L_THREADS) {
-        double r[LW];
-        double* row = M + (long long)i * ld + j0;
+        // accumulators start at -Sigma (so that W = -(acc + A B^T ...) needs no negated operand): entries re-computed from
+        // the coordinates while the first operand stage is in flight
+        double acc[2][4][2];
+        const bool plain = (t > 0) && (i0 + LTM <= k);  // every row is a matrix row below the diagonal block
 #pragma unroll
-        for (int cc = 0; cc < LW; ++cc) r[cc] = (cc < w) ? row[cc] : 0.0;
+        for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-        for (int cc = 0; cc < LW; ++cc) {
-          double s = r[cc];
+          for (int ni = 0; ni < 4; ++ni)
 #pragma unroll
-          for (int t = 0; t < cc; ++t) s -= r[t] * Ds[cc][t];
-          r[cc] = s / Ds[cc][cc];
-        }
-#pragma unroll
-        for (int cc = 0; cc < LW; ++cc)
-          if (cc < w) row[cc] = r[cc];
-      }
-      __syncthreads();
-      // trailing update: M[i][cc] -= sum_t P[i][t] P[cc][t], i >= j0+w, j0+w <= cc < k, cc <= i for matrix rows
-      const int t0 = j0 + w;
-      if (t0 < k) {
-        const int tx = tid & 15, ty = tid >> 4;
-        for (int ti = t0; ti < R; ti += LT) {
-          for (int tc = t0; tc < k && tc <= ti + LT - 1; tc += LT) {
-            for (int e = tid; e < LT * LW; e += L_THREADS) {
-              const int rr = e / LW, cc = e % LW;
-              Pa[rr][cc] = (ti + rr < R && cc < w) ? M[(long long)(ti + rr) * ld + j0 + cc] : 0.0;
-              Pb[rr][cc] = (tc + rr < k && cc < w) ? M[(long long)(tc + rr) * ld + j0 + cc] : 0.0;
+            for (int e = 0; e < 2; ++e) {
+              const int i = wrow + 8 * mi + g4, j = c0 + 8 * ni + 2 * t4 + e;
+              double v;
+              if (plain) v = local_cov_entry<METRIC, FAST>(g, i, j, k0, pa, pb, pc);
+              else v = (i < R) ? local_entry<METRIC, FAST>(g, i, j, k, kp, k0, pa, pb, pc, pcv, pzv) : 0.0;
+              acc[mi][ni][e] = -v;
             }
+        if (KT > 0) {
+          int rd = 0, wr = LSTG - 1;
+          for (int kt = 0; kt < KT; ++kt) {
+            l_cp_wait<LSTG - 2>();
             __syncthreads();
-            double acc[4][4];
+            load_stage(wr, kt + LSTG - 1);
+            l_cp_commit();
+            const double* As = stage + rd * L_STAGE_ELEMS + (16 * warp + g4) * LLD + t4;
+            const double* Bs = stage + rd * L_STAGE_ELEMS + (LTM + g4) * LLD + t4;
 #pragma unroll
-            for (int r_ = 0; r_ < 4; ++r_)
+            for (int kk = 0; kk < LK; kk += 4) {
+              double a[2], b[4];
 #pragma unroll
-              for (int q_ = 0; q_ < 4; ++q_) acc[r_][q_] = 0.0;
-#pragma unroll 8
-            for (int t = 0; t < LW; ++t) {
-              double av[4], bv[4];
+              for (int mi = 0; mi < 2; ++mi) a[mi] = As[mi * 8 * LLD + kk];
 #pragma unroll
-              for (int r_ = 0; r_ < 4; ++r_) av[r_] = Pa[ty + 16 * r_][t];
+              for (int ni = 0; ni < 4; ++ni) b[ni] = Bs[ni * 8 * LLD + kk];
 #pragma unroll
-              for (int q_ = 0; q_ < 4; ++q_) bv[q_] = Pb[tx + 16 * q_][t];
+              for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-              for (int r_ = 0; r_ < 4; ++r_)
-#pragma unroll
-                for (int q_ = 0; q_ < 4; ++q_) acc[r_][q_] += av[r_] * bv[q_];
+                for (int ni = 0; ni < 4; ++ni) l_dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
             }
+            rd = (rd + 1 == LSTG) ? 0 : rd + 1;
+            wr = (wr + 1 == LSTG) ? 0 : wr + 1;
+          }
+          l_cp_wait<0>();
+          __syncthreads();  // every warp is done with the staging buffers: W may overwrite them
+        }
+        // W tile -> shared memory (A-operand layout of the panel product)
 #pragma unroll
-            for (int r_ = 0; r_ < 4; ++r_)
+        for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-              for (int q_ = 0; q_ < 4; ++q_) {
-                const int i = ti + ty + 16 * r_, cc = tc + tx + 16 * q_;
-                if (i < R && cc < k && (cc <= i)) M[(long long)i * ld + cc] -= acc[r_][q_];
+          for (int ni = 0; ni < 4; ++ni)
+            *reinterpret_cast<double2*>(Wt + (16 * warp + 8 * mi + g4) * LWLD + 8 * ni + 2 * t4) =
+                make_double2(-acc[mi][ni][0], -acc[mi][ni][1]);
+        if (t == 0) {
+          __syncthreads();
+          if (warp == 0) {
+            // ---- D = L_d L_d^T, lane = row; a[kk] holds the UNSCALED column entry until column kk is finished
+            double a[LP];
+#pragma unroll
+            for (int kk = 0; kk < LP; ++kk) a[kk] = Wt[lane * LWLD + kk];
+            int first_bad = 0;
+            double dk = 1.0;
+#pragma unroll
+            for (int kk = 0; kk < LP; ++kk) {
+              const double d = __shfl_sync(0xffffffffu, a[kk], kk);
+              if (!(d > 0.0) && first_bad == 0) first_bad = c0 + kk + 1;
+              if (lane == kk) dk = d;
+              double invd;
+              asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(invd) : "d"(d));
+              invd = fma(fma(-d, invd, 1.0), invd, invd);
+              invd = fma(fma(-d, invd, 1.0), invd, invd);
+              const double u = a[kk];
+              const double w = u * invd;
+#pragma unroll
+              for (int jj = kk + 1; jj < LP; ++jj) {
+                const double ujk = __shfl_sync(0xffffffffu, u, jj);
+                a[jj] = fma(-w, ujk, a[jj]);
               }
-            __syncthreads();
+            }
+            const double sqv = sqrt(dk);
+            const double rsv = 1.0 / sqv;
+            rsd[lane] = rsv;
+            if (lane == 0 && first_bad != 0 && s_fail == 0) s_fail = first_bad;
+#pragma unroll
+            for (int kk = 0; kk < LP; ++kk) {
+              const double rs = __shfl_sync(0xffffffffu, rsv, kk);
+              if (kk <= lane) Wt[lane * LWLD + kk] = (lane == kk) ? sqv : a[kk] * rs;
+            }
+            __syncwarp();
+            // ---- X_d = L_d^-1, lane = column: forward substitution on e_lane, L_d read by broadcast
+            double x[LP];
+#pragma unroll
+            for (int i = 0; i < LP; ++i) x[i] = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+            for (int kk = 0; kk < LP; ++kk) {
+              x[kk] *= rsd[kk];
+#pragma unroll
+              for (int i = kk + 1; i < LP; ++i) x[i] = fma(-Wt[i * LWLD + kk], x[kk], x[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < LP; ++i) Xd[i * LWLD + lane] = x[i];
+          }
+          __syncthreads();
+        } else {
+          __syncwarp();
+        }
+        // ---- panel: P = W X_d^T for the rows below the diagonal block; column tile ni only needs k <= 8 ni + 7
+        if (t > 0 || warp >= 2) {
+          double out[2][4][2];
+          const double* Aw = Wt + (16 * warp + g4) * LWLD + t4;
+#pragma unroll
+          for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) {
+              out[mi][ni][0] = 0.0;
+              out[mi][ni][1] = 0.0;
+            }
+#pragma unroll
+          for (int ks = 0; ks < LP / 4; ++ks) {
+            double a[2];
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi) a[mi] = Aw[mi * 8 * LWLD + 4 * ks];
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) {
+              if (4 * ks > 8 * ni + 7) continue;  // X_d is lower triangular
+              const double b = Xd[(8 * ni + g4) * LWLD + 4 * ks + t4];
+#pragma unroll
+              for (int mi = 0; mi < 2; ++mi) l_dmma(out[mi][ni][0], out[mi][ni][1], a[mi], b);
+            }
+          }
+#pragma unroll
+          for (int mi = 0; mi < 2; ++mi) {
+            const int i = wrow + 8 * mi + g4;
+            if (i < R) {
+              double* dst = Lw + (long long)i * ld + c0 + 2 * t4;
+#pragma unroll
+              for (int ni = 0; ni < 4; ++ni) *reinterpret_cast<double2*>(dst + 8 * ni) = make_double2(out[mi][ni][0], out[mi][ni][1]);
+            }
           }
         }
       }
     }
-    // ---- 4. prediction ----
+    __syncthreads();
+    // ---- 3. prediction: rows kp (v = L^-1 c) and kp + 1 (y = L^-1 z) of the factor array
     double sv = 0.0, sy = 0.0;
-    for (int b = tid; b < k; b += L_THREADS) {
-      const double v = M[(long long)k * ld + b], y = M[(long long)(k + 1) * ld + b];
-      sv += v * v;
-      sy += v * y;
+    {
+      const double* vrow = Lw + (long long)kp * ld;
+      const double* yrow = vrow + ld;
+      for (int b = tid; b < kp; b += L_THREADS) {
+        const double v = vrow[b], y = yrow[b];
+        sv = fma(v, v, sv);
+        sy = fma(v, y, sy);
+      }
     }
     red[tid] = sv;
     __syncthreads();
@@ -248,16 +471,19 @@ __global__ void __launch_bounds__(L_THREADS) ck_local_predict_kernel(LocalArgs g
         g.pred[c] = sy; g.sd[c] = sd; g.info[c] = (var > 0.0) ? 0 : -1;  // -1: augmented matrix not PD (warning only)
       }
     }
-    __syncthreads();
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
 static int local_fill(LocalArgs* g, const double* xy0, const double* z0, ck_i64 n0, const double* xy1, const double* z1,
-                      ck_i64 n1, const double* xyp, ck_i64 m, const double* params, int n_procs, int i_pred, int metric,
-                      double max_dist, int cv) {
-  CkParams p;
-  int rc = ck_unpack_params(params, n_procs, &p);
+                      ck_i64 n1, const double* xyp, ck_i64 m, const double* params_sigma, const double* params_pred,
+                      int n_procs, int i_pred, int metric, double max_dist, int cv) {
+  CkParams ps, pp;
+  int rc = ck_unpack_params(params_sigma, n_procs, &ps);
   if (rc) return rc;
+  if ((rc = ck_unpack_params(params_pred ? params_pred : params_sigma, n_procs, &pp))) return rc;
   CK_REQUIRE(i_pred >= 0 && i_pred < n_procs, "i_pred out of range");
   CK_REQUIRE(metric == CK_METRIC_EUCLID || metric == CK_METRIC_HAVERSINE, "bad metric %d", metric);
   CK_REQUIRE(n0 >= 0 && n1 >= 0 && m >= 0, "negative size");
@@ -265,62 +491,121 @@ static int local_fill(LocalArgs* g, const double* xy0, const double* z0, ck_i64 
   g->xy[0] = xy0; g->z[0] = z0; g->n[0] = n0;
   g->xy[1] = xy1; g->z[1] = z1; g->n[1] = (n_procs == 2) ? n1 : 0;
   g->xyp = xyp; g->m = m;
-  for (int i = 0; i < n_procs; ++i)
-    for (int j = 0; j < n_procs; ++j)
-      if ((rc = ck_block_matern(p, i, j, 1, &g->S[i][j]))) return rc;
+  if ((rc = ck_block_matern(ps, 0, 0, 1, &g->S[0]))) return rc;
+  if (n_procs == 2) {
+    if ((rc = ck_block_matern(ps, 0, 1, 1, &g->S[1]))) return rc;
+    if ((rc = ck_block_matern(ps, 1, 1, 1, &g->S[2]))) return rc;
+  } else {
+    g->S[1] = g->S[0];
+    g->S[2] = g->S[0];
+  }
   for (int j = 0; j < n_procs; ++j)
-    if ((rc = ck_block_matern(p, i_pred, j, 1, &g->C[j]))) return rc;
+    if ((rc = ck_block_matern(pp, i_pred, j, 1, &g->C[j]))) return rc;
   g->n_procs = n_procs; g->i_pred = i_pred; g->metric = metric; g->cv = cv;
   g->max_dist = max_dist;
-  g->c0 = p.sigma[i_pred] * p.sigma[i_pred] + p.nugget[i_pred];  // covariance(i, 0, use_nugget=True), src/point_prediction.py:66
   return CK_OK;
 }
 
-static inline long long local_slots(ck_i64 m) { return m < 148 * 2 ? (m > 0 ? m : 1) : 148 * 2; }
-static inline long long local_ldk(ck_i64 kmax) { return (kmax + 15) / 16 * 16; }
+struct LocalPlan {
+  long long kmax, kmaxp, slots, slot_stride;  // slot_stride in doubles
+  int pts_in_ws;
+  size_t smem;
+};
+
+static LocalPlan local_plan(ck_i64 m, ck_i64 kmax, int metric) {
+  LocalPlan p;
+  p.kmax = kmax > 0 ? kmax : 1;
+  p.kmaxp = (p.kmax + LP - 1) / LP * LP;
+  p.pts_in_ws = p.kmax > L_SMEM_KMAX ? 1 : 0;
+  const long long kcap = (p.kmax + 7) / 8 * 8;
+  const long long rec = 5 * kcap;  // a, b, c-vector, z, cos(lat)
+  p.slot_stride = (p.kmaxp + 2) * p.kmaxp + (p.pts_in_ws ? rec : 0);
+  p.slot_stride = (p.slot_stride + 31) / 32 * 32;
+  long long slots = 148 * 4;
+  const long long budget = (8LL << 30) / 8;  // at most 8 GB of factor slots
+  if (slots * p.slot_stride > budget) slots = budget / p.slot_stride;
+  if (slots < 148) slots = 148;
+  if (slots > m) slots = m > 0 ? m : 1;
+  p.slots = slots;
+  const long long narr = (metric == CK_METRIC_HAVERSINE) ? 5 : 4;
+  p.smem = (size_t)(LSTG * L_STAGE_ELEMS + LP * LWLD + LP + L_THREADS + (p.pts_in_ws ? 0 : narr * kcap)) * sizeof(double);
+  return p;
+}
 
 extern "C" size_t ck_local_predict_workspace_bytes(ck_i64 m, ck_i64 kmax) {
   if (m <= 0 || kmax <= 0) return 256;
-  const size_t slots = (size_t)local_slots(m);
-  return slots * ((size_t)(kmax + 2) * (size_t)local_ldk(kmax) + (size_t)kmax * 4) * sizeof(double) + 256;
+  const LocalPlan p = local_plan(m, kmax, CK_METRIC_HAVERSINE);
+  return (size_t)p.slots * (size_t)p.slot_stride * sizeof(double) + 256;
 }
 
 extern "C" int ck_local_count(const double* xy0, ck_i64 n0, const double* xy1, ck_i64 n1, const double* xyp, ck_i64 m,
-                              int n_procs, int i_pred, int metric, double max_dist, int cv, int* k_dev, void* stream) {
+                              int n_procs, int i_pred, int metric, double max_dist, int cv, int* k_dev, int* seg_dev,
+                              void* stream) {
   static const double dummy1[4] = {1, 1.5, 1, 0}, dummy2[11] = {1, 1, 1.5, 1.5, 1.5, 1, 1, 1, 0, 0, 0};
   LocalArgs g;
-  int rc = local_fill(&g, xy0, nullptr, n0, xy1, nullptr, n1, xyp, m, n_procs == 1 ? dummy1 : dummy2, n_procs, i_pred,
+  int rc = local_fill(&g, xy0, nullptr, n0, xy1, nullptr, n1, xyp, m, n_procs == 1 ? dummy1 : dummy2, nullptr, n_procs, i_pred,
                       metric, max_dist, cv);
   if (rc) return rc;
   if (m == 0) return CK_OK;
-  CK_REQUIRE(k_dev && xyp, "null pointer");
-  const unsigned grid = (unsigned)(m < 148 * 8 ? m : 148 * 8);
+  CK_REQUIRE(k_dev && seg_dev && xyp, "null pointer");
+  CK_REQUIRE((((uintptr_t)xy0 | (uintptr_t)xy1) & 15) == 0, "coordinate arrays must be 16-byte aligned");
+  const unsigned grid = (unsigned)(m < 148 * 16 ? m : 148 * 16);
   cudaStream_t st = ck_stream(stream);
-  if (metric == CK_METRIC_HAVERSINE) ck_local_count_kernel<CK_METRIC_HAVERSINE><<<grid, L_THREADS, 0, st>>>(g, k_dev);
-  else ck_local_count_kernel<CK_METRIC_EUCLID><<<grid, L_THREADS, 0, st>>>(g, k_dev);
+  if (metric == CK_METRIC_HAVERSINE) ck_local_count_kernel<CK_METRIC_HAVERSINE><<<grid, L_THREADS, 0, st>>>(g, k_dev, seg_dev);
+  else ck_local_count_kernel<CK_METRIC_EUCLID><<<grid, L_THREADS, 0, st>>>(g, k_dev, seg_dev);
   CK_LAUNCH_CHECK();
   return CK_OK;
 }
 
-extern "C" int ck_local_predict(const double* xy0, const double* z0, ck_i64 n0, const double* xy1, const double* z1,
-                                ck_i64 n1, const double* xyp, ck_i64 m, const double* params, int n_procs, int i_pred,
-                                int metric, double max_dist, int cv, const int* k_dev, ck_i64 kmax, double* pred,
-                                double* sd, int* info, void* ws, void* stream) {
-  LocalArgs g;
-  int rc = local_fill(&g, xy0, z0, n0, xy1, z1, n1, xyp, m, params, n_procs, i_pred, metric, max_dist, cv);
-  if (rc) return rc;
-  if (m == 0) return CK_OK;
-  CK_REQUIRE(k_dev && pred && sd && info && xyp, "null pointer");
-  CK_REQUIRE(kmax >= 0, "negative kmax");
-  CK_REQUIRE(kmax == 0 || ws, "workspace is NULL");
-  const long long slots = local_slots(m);
-  g.kcount = k_dev; g.kmax = kmax > 0 ? kmax : 1; g.ldk = local_ldk(g.kmax);
-  g.pred = pred; g.sd = sd; g.info = info;
-  g.ws_mat = static_cast<double*>(ws);
-  g.ws_pts = g.ws_mat + (size_t)slots * (size_t)(g.kmax + 2) * (size_t)g.ldk;
-  cudaStream_t st = ck_stream(stream);
-  if (metric == CK_METRIC_HAVERSINE) ck_local_predict_kernel<CK_METRIC_HAVERSINE><<<(unsigned)slots, L_THREADS, 0, st>>>(g);
-  else ck_local_predict_kernel<CK_METRIC_EUCLID><<<(unsigned)slots, L_THREADS, 0, st>>>(g);
+template <int METRIC, int FAST>
+static int local_launch(const LocalArgs& g, const LocalPlan& p, cudaStream_t st) {
+  static CkPerDevice attr;
+  CK_SET_SMEM_ONCE(attr, (ck_local_predict_kernel<METRIC, FAST>), 200 * 1024);
+  ck_local_predict_kernel<METRIC, FAST><<<(unsigned)p.slots, L_THREADS, p.smem, st>>>(g);
   CK_LAUNCH_CHECK();
   return CK_OK;
+}
+
+template <int METRIC>
+static int local_dispatch(const LocalArgs& g, const LocalPlan& p, cudaStream_t st) {
+  const int mode = g.S[0].mode;
+  const bool uniform = mode != CK_NU_GENERIC && g.S[1].mode == mode && g.S[2].mode == mode;
+  if (uniform) {
+    switch (mode) {
+      case CK_NU_HALF: return local_launch<METRIC, CK_NU_HALF>(g, p, st);
+      case CK_NU_3HALF: return local_launch<METRIC, CK_NU_3HALF>(g, p, st);
+      case CK_NU_5HALF: return local_launch<METRIC, CK_NU_5HALF>(g, p, st);
+      default: return local_launch<METRIC, CK_NU_7HALF>(g, p, st);
+    }
+  }
+  return local_launch<METRIC, L_FAST_NONE>(g, p, st);
+}
+
+extern "C" int ck_local_predict(const double* xy0, const double* z0, ck_i64 n0, const double* xy1, const double* z1,
+                                ck_i64 n1, const double* xyp, ck_i64 m, const double* params_sigma, const double* params_pred,
+                                int n_procs, int i_pred, int metric, double max_dist, int cv, double c0, const int* k_dev,
+                                const int* seg_dev, ck_i64 kmax, double* pred, double* sd, int* info, void* ws, void* stream) {
+  LocalArgs g;
+  int rc = local_fill(&g, xy0, z0, n0, xy1, z1, n1, xyp, m, params_sigma, params_pred, n_procs, i_pred, metric, max_dist, cv);
+  if (rc) return rc;
+  if (m == 0) return CK_OK;
+  CK_REQUIRE(k_dev && seg_dev && pred && sd && info && xyp, "null pointer");
+  CK_REQUIRE(kmax >= 0, "negative kmax");
+  CK_REQUIRE(ws, "workspace is NULL");
+  CK_REQUIRE((((uintptr_t)xy0 | (uintptr_t)xy1 | (uintptr_t)ws) & 15) == 0, "coordinate arrays / workspace must be 16-byte aligned");
+  const LocalPlan p = local_plan(m, kmax, metric);
+  CK_REQUIRE(p.smem <= 200 * 1024, "kmax too large for the shared-memory plan");
+  g.c0 = c0;
+  g.kcount = k_dev; g.kseg = seg_dev; g.kmax = p.kmax; g.kmaxp = p.kmaxp;
+  g.pred = pred; g.sd = sd; g.info = info;
+  // the last 256 bytes of the workspace hold the target counter of the persistent CTAs
+  char* wsb = static_cast<char*>(ws);
+  g.counter = reinterpret_cast<unsigned int*>(wsb + (size_t)p.slots * (size_t)p.slot_stride * sizeof(double));
+  g.ws = static_cast<double*>(ws);
+  g.slot_stride = p.slot_stride;
+  g.pts_in_ws = p.pts_in_ws;
+  cudaStream_t st = ck_stream(stream);
+  CK_CUDA(cudaMemsetAsync(g.counter, 0, sizeof(unsigned int), st));
+  if (metric == CK_METRIC_HAVERSINE) return local_dispatch<CK_METRIC_HAVERSINE>(g, p, st);
+  return local_dispatch<CK_METRIC_EUCLID>(g, p, st);
 }

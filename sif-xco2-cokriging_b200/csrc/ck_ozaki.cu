@@ -492,15 +492,8 @@ extern "C" int ck_oz_split(const double* src, ck_i64 ld, ck_i64 rows, ck_i64 k, 
   const ck_i64 rows_b_pad = ((rows + OZ_TN - 1) / OZ_TN) * OZ_TN;
   const int vec = ((((uintptr_t)src) & 15) == 0 && (ld & 1) == 0) ? 1 : 0;
   const size_t smem = (size_t)(k / 16) * OZ_S * 128;  // <= 56 KB
-  {
-    static bool attr_done[64] = {};
-    int dev = 0;
-    CK_CUDA(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-      CK_CUDA(cudaFuncSetAttribute(ck_oz_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * OZ_S * 128));
-      if (dev >= 0 && dev < 64) attr_done[dev] = true;
-    }
-  }
+  static CkPerDevice attr;
+  CK_SET_SMEM_ONCE(attr, ck_oz_split_kernel, 64 * OZ_S * 128);
   ck_oz_split_kernel<<<(unsigned)(rows_pad / 8), 256, smem, ck_stream(stream)>>>(src, ld, rows, (int)k, static_cast<uint8_t*>(fmt_a),
                                                                             static_cast<uint8_t*>(fmt_b), rows_b_pad, scales, vec);
   CK_LAUNCH_CHECK();
@@ -511,20 +504,6 @@ static long long* g_oz_dbg = nullptr;
 extern "C" int ck_oz_debug_buffer(void* dev_counters) {
   g_oz_dbg = static_cast<long long*>(dev_counters);
   return CK_OK;
-}
-
-// Upper bound on the CTAs (= SMs) of the next ck_oz_gemm / ck_oz_mg_update launches (0 = every SM).  Lets a caller that
-// runs two streams (block-cyclic look-ahead) split the machine between a panel stream and the trailing update.
-static int g_oz_max_ctas = 0;
-extern "C" int ck_oz_set_grid(int max_ctas) {
-  g_oz_max_ctas = max_ctas > 0 ? max_ctas : 0;
-  return CK_OK;
-}
-
-int ck_oz_grid_swap(int max_ctas) {  // internal (ck_common.cuh): set the cap, return the previous one
-  const int old = g_oz_max_ctas;
-  g_oz_max_ctas = max_ctas > 0 ? max_ctas : 0;
-  return old;
 }
 
 static int oz_num_sms() {
@@ -540,22 +519,15 @@ int ck_oz_num_sms() { return oz_num_sms(); }
 
 static int oz_gemm_launch(const void* a_slices, const double* sa, ck_i64 m, const void* b_slices, const double* sb, ck_i64 n,
                           ck_i64 k, double* c, ck_i64 ldc, int lower, ck_i64 tb, ck_i64 gi0, ck_i64 gis, ck_i64 gj0, ck_i64 gjs,
-                          void* stream) {
+                          int max_ctas, void* stream) {
   CK_REQUIRE(m >= 0 && n >= 0 && k >= 0, "negative size");
   if (m == 0 || n == 0 || k == 0) return CK_OK;
   CK_REQUIRE(a_slices && b_slices && sa && sb && c, "null pointer");
   CK_REQUIRE(k % OZ_KC == 0 && k <= 1024, "k (%lld) must be a multiple of 32 and <= 1024", (long long)k);
   CK_REQUIRE(ldc >= n, "ldc (%lld) < n (%lld)", (long long)ldc, (long long)n);
   CK_REQUIRE((((uintptr_t)a_slices | (uintptr_t)b_slices) & 15) == 0, "slice buffers must be 16-byte aligned");
-  {
-    static bool attr_done[64] = {};  // the attribute is per device
-    int dev = 0;
-    CK_CUDA(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-      CK_CUDA(cudaFuncSetAttribute(ck_oz_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM));
-      if (dev >= 0 && dev < 64) attr_done[dev] = true;
-    }
-  }
+  static CkPerDevice attr;
+  CK_SET_SMEM_ONCE(attr, ck_oz_gemm_kernel, OZ_SMEM);
   OzGemmArgs g;
   g.a = static_cast<const uint8_t*>(a_slices);
   g.b = static_cast<const uint8_t*>(b_slices);
@@ -580,7 +552,7 @@ static int oz_gemm_launch(const void* a_slices, const double* sa, ck_i64 m, cons
   g.vec = ((((uintptr_t)c) & 15) == 0 && (ldc & 1) == 0) ? 1 : 0;
   g.dbg = g_oz_dbg;
   long long grid = oz_num_sms();
-  if (g_oz_max_ctas > 0 && grid > g_oz_max_ctas) grid = g_oz_max_ctas;
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;  // caller leaves SMs to a concurrent stream (look-ahead)
   if (grid > g.nvirt) grid = g.nvirt;
   ck_oz_gemm_kernel<<<(unsigned)grid, OZ_THREADS, OZ_SMEM, ck_stream(stream)>>>(g);
   CK_LAUNCH_CHECK();
@@ -588,16 +560,16 @@ static int oz_gemm_launch(const void* a_slices, const double* sa, ck_i64 m, cons
 }
 
 extern "C" int ck_oz_gemm(const void* a_slices, const double* sa, ck_i64 m, const void* b_slices, const double* sb, ck_i64 n,
-                          ck_i64 k, double* c, ck_i64 ldc, int lower, void* stream) {
-  return oz_gemm_launch(a_slices, sa, m, b_slices, sb, n, k, c, ldc, lower, 0, 0, 1, 0, 1, stream);
+                          ck_i64 k, double* c, ck_i64 ldc, int lower, int max_ctas, void* stream) {
+  return oz_gemm_launch(a_slices, sa, m, b_slices, sb, n, k, c, ldc, lower, 0, 0, 1, 0, 1, max_ctas, stream);
 }
 
 extern "C" int ck_oz_mg_update(const void* a_slices, const double* sa, ck_i64 m, const void* b_slices, const double* sb, ck_i64 n,
                                ck_i64 k, double* c, ck_i64 ldc, ck_i64 tb, ck_i64 row_tile0, ck_i64 row_tile_step, ck_i64 col_tile0,
-                               ck_i64 col_tile_step, void* stream) {
+                               ck_i64 col_tile_step, int max_ctas, void* stream) {
   CK_REQUIRE(tb > 0 && tb % 128 == 0, "tile size must be a multiple of 128 (got %lld)", (long long)tb);
   CK_REQUIRE(m % tb == 0 && n % tb == 0, "m and n must be whole tiles");
   CK_REQUIRE(row_tile_step >= 1 && col_tile_step >= 1 && row_tile0 >= 0 && col_tile0 >= 0, "bad tile map");
   return oz_gemm_launch(a_slices, sa, m, b_slices, sb, n, k, c, ldc, 0, tb, row_tile0, row_tile_step, col_tile0, col_tile_step,
-                        stream);
+                        max_ctas, stream);
 }

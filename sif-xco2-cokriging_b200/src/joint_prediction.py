@@ -10,9 +10,13 @@ The N x N matrix is never brought to the host.  Differences in *how* (not what) 
   * one triangular solve instead of cho_solve + two matmuls: pred = (L^-1 c).(L^-1 z),
     var = c0 - |L^-1 c|^2, c0 = sigma_i^2 + nugget_i (the diagonal of the reference's ``pred_cov``);
   * the reference's ``_verify_model`` factors the augmented (m+N)^2 matrix only to emit a warning
-    (:60-66, :260-274); here the same warning is raised from the Schur complement: any predictive
-    variance <= 0 means the augmented matrix is not positive definite (necessary condition only --
-    a non-PD m x m Schur complement with positive diagonal is not detected);
+    (:60-66, :260-274).  Block Cholesky: that matrix is PD  <=>  Sigma is PD and the m x m Schur
+    complement C_pp - V V^T (V = L^-1 C_dp, already computed by the solve) is PD.  For
+    m <= ``Predictor.verify_max_targets`` (4096) the Schur complement is formed and factored on the
+    device (m^2 N + m^3/3 flops instead of (m+N)^3/3) -- the exact test.  Above that size only the
+    necessary condition "every predictive variance > 0" (the diagonal of the Schur complement) is
+    checked: a non-PD Schur complement with a positive diagonal goes undetected there.  When Sigma
+    itself is not PD the warning is emitted and LinAlgError raised, like the reference;
   * ``cross_validation`` uses the closed-form leave-one-out identities from ONE factorisation
     (pred_k = z_k - (S^-1 z)_k / (S^-1)_kk, sd_k = (S^-1)_kk^-1/2) instead of n_i re-assemblies
     and re-factorisations (:207-257); equal to the reference loop up to rounding.
@@ -31,8 +35,15 @@ from fields import MultiField, distance_matrix  # noqa: F401
 from model import MultivariateMatern
 
 
+INVALID_MODEL = "Prediction joint covariance matrix is not positive definte; model technically invalid."
+
+
 class Predictor:
     """Multivariate prediction framework."""
+
+    # largest number of targets for which the exact positive-definiteness test of the augmented matrix is run
+    # (Cholesky of the m x m Schur complement); above it only the diagonal (predictive variances) is tested
+    verify_max_targets = 4096
 
     def __init__(self, mod: MultivariateMatern, mf: MultiField, covariates=None, dist_units: str = "km",
                  fast_dist: bool = True) -> None:
@@ -58,17 +69,33 @@ class Predictor:
         return [ops.coords_to_device(c) for c in coords], ops.to_device(np.hstack(values))
 
     def _solve(self, pcoords: np.ndarray, cv_ix: int = None):
-        """(pred, var) numpy arrays at the rows of `pcoords`; raises LinAlgError if Sigma is not PD."""
-        params = self.mod.params.get_values()
+        """(pred, var, valid) at the rows of `pcoords`: numpy arrays and whether the reference's augmented matrix
+        [[C_pp, C_dp^T], [C_dp, Sigma]] is positive definite (None when not tested: cross-validation calls).
+        Raises LinAlgError if Sigma is not PD."""
+        p = self.mod.params
+        params = p.get_values()
         metric = self._metric()
         coords_d, z_d = self._device_data(cv_ix)
         sigma = ops.joint_cov(coords_d, params, self.n_procs, metric)
         factor = ops.potrf(sigma)
-        cpd = ops.cross_cov(coords_d, ops.coords_to_device(pcoords), params, self.n_procs, self.i, metric)
-        c0 = self.mod.params.sigma.values[self.i, self.i] ** 2 + self.mod.params.nugget.values[self.i, self.i]
+        pc_d = ops.coords_to_device(pcoords)
+        cpd = ops.cross_cov(coords_d, pc_d, params, self.n_procs, self.i, metric)
+        c0 = p.sigma.values[self.i, self.i] ** 2 + p.nugget.values[self.i, self.i]
         pred, var = factor.predict(cpd, z_d, c0)
-        factor.raise_if_failed()  # the reference lets LinAlgError propagate from the real solve (:68-73)
-        return pred.cpu().numpy(), var.cpu().numpy()
+        if factor.info != 0:
+            if cv_ix is None:  # the reference's _verify_model fails first (warning), then cho_factor raises (:60-73)
+                warnings.warn(INVALID_MODEL)
+            factor.raise_if_failed()
+        pred, var = pred.cpu().numpy(), var.cpu().numpy()
+        valid = None
+        if cv_ix is None:
+            valid = not (var <= 0.0).any()  # diagonal of the Schur complement: necessary
+            m = pc_d.shape[0]
+            if valid and m <= self.verify_max_targets:  # exact: Cholesky of C_pp - V V^T
+                cpp = ops.matern_block(pc_d, pc_d, metric, p.sigma.values[self.i, self.i] ** 2, p.nu.values[self.i, self.i],
+                                       p.len_scale.values[self.i, self.i], p.nugget.values[self.i, self.i], symmetric=True)
+                valid = factor.schur_info(cpd[:m], cpp) == 0
+        return pred, var, valid
 
     def predict_frame(self, i: int, pcoords, cv_ix: int = None) -> pd.DataFrame:
         """Predictions and prediction standard errors as a DataFrame: the columns of `pcoords`
@@ -78,9 +105,9 @@ class Predictor:
             pcoords = pd.DataFrame({"d1": np.atleast_1d(pcoords)[0], "d2": np.atleast_1d(pcoords)[1]}, index=[0])
         elif not isinstance(pcoords, pd.DataFrame):
             pcoords = pd.DataFrame(np.atleast_2d(np.asarray(pcoords, dtype=float)), columns=["d1", "d2"])
-        pred, var = self._solve(pcoords.values.astype(float), cv_ix=cv_ix)
-        if cv_ix is None and (var <= 0.0).any():
-            warnings.warn("Prediction joint covariance matrix is not positive definte; model technically invalid.")
+        pred, var, valid = self._solve(pcoords.values.astype(float), cv_ix=cv_ix)
+        if valid is False:
+            warnings.warn(INVALID_MODEL)
         df_pred = pcoords.copy()
         df_pred["pred"] = pred
         with np.errstate(invalid="ignore"):

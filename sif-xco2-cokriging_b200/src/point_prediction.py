@@ -10,8 +10,13 @@ the local covariance from coordinates, factors and solves.  ``partitions`` is ac
 Same outputs and corner cases: ``(nan, nan)`` with a warning when no datum lies within ``max_dist``
 or when the local matrix is not positive definite; ``pred_err = nanmax(sqrt(c0 - w.c), 0)``;
 "Invalid model" warning when the augmented matrix is not PD (kriging variance <= 0, the Schur
-complement of the reference's (1+k)^2 check).  ``Sigma`` (dict of host blocks "00", "01", "11") is
-assembled lazily on first access, since the device path does not need it.
+complement of the reference's (1+k)^2 check -- or the local matrix itself not PD).
+
+Which parameters are used where follows the reference exactly: the joint covariance ``Sigma`` is
+frozen when the Predictor is constructed (:42) -- the parameter values are snapshotted in
+``__init__`` and both the lazily assembled host blocks ``Sigma`` ("00", "01", "11") and the local
+matrices inside the kernel are built from that snapshot -- while ``c0`` (:66) and the
+target-to-neighbour covariance vector (:115-125) use the model's parameters at call time.
 """
 from __future__ import annotations
 
@@ -43,6 +48,7 @@ class Predictor:
         self.dist_units = dist_units
         self.fast_dist = fast_dist
         self._Sigma = None
+        self._sigma_params = np.array(mod.params.get_values(), dtype=float)  # Sigma is frozen here (reference :42)
         self.cv = False  # placeholder for cross-validation
 
     def _metric(self) -> int:
@@ -57,7 +63,8 @@ class Predictor:
 
     def _cov_blocks(self) -> dict:
         """Each block of the block-covariance matrix (within a process or between processes)."""
-        p = self.mod.params
+        import copy
+        p = copy.deepcopy(self.mod.params).set_values(self._sigma_params)  # the snapshot taken at construction
         metric = self._metric()
         X = [ops.coords_to_device(np.asarray(f.coords_main, dtype=float)) for f in self.mf.fields]
         blocks = dict()
@@ -144,11 +151,12 @@ class Predictor:
         pc = df_chunk.iloc[:, :2].values.astype(float)
         coords = [ops.coords_to_device(np.asarray(f.coords_main, dtype=float)) for f in self.mf.fields]
         values = [ops.to_device(np.asarray(f.values_main, dtype=float)) for f in self.mf.fields]
-        pred, sd, k, info = ops.local_predict(coords, values, ops.coords_to_device(pc), self.mod.params.get_values(),
-                                              self.n_procs, self.i, self._metric(), max_dist, cv=self.cv)
+        pred, sd, k, info = ops.local_predict(coords, values, ops.coords_to_device(pc), self._sigma_params,
+                                              self.n_procs, self.i, self._metric(), max_dist, cv=self.cv,
+                                              params_pred=self.mod.params.get_values(), c0=float(c0))
         for row in np.flatnonzero(k == 0):
             warnings.warn(f"No data within maximum distance {max_dist} at location {pc[row]}.")
-        for row in np.flatnonzero(info == -1):
+        for row in np.flatnonzero(info != 0):  # augmented matrix not PD: Schur complement <= 0 or Sigma_loc itself not PD
             warnings.warn(f"Invalid model at prediction location {pc[row]}. This can happen at data locations.")
         if (info > 0).any():
             warnings.warn("Local covariance matrix not positive definte; returning NaN.")

@@ -94,7 +94,7 @@ def test_int8_product_equals_fp64_product(lib, m, n, k, lower, wide):
     fa, _, sa = _split(lib, torch.from_numpy(a).cuda(), True, False)
     _, fb, sb = _split(lib, torch.from_numpy(b).cuda(), False, True)
     lib.check(lib.lib.ck_oz_gemm(fa.data_ptr(), sa.data_ptr(), m, fb.data_ptr(), sb.data_ptr(), n, k, cbuf.data_ptr(), ldc,
-                                 int(lower), _stream()), "ck_oz_gemm")
+                                 int(lower), 0, _stream()), "ck_oz_gemm")
     torch.cuda.synchronize()
     got = cbuf[:, :n].cpu().numpy()
     # every entry against the FP64 numpy product: the bound is dominated by the rounding of that reference itself
@@ -122,7 +122,7 @@ def test_int8_product_rejects_bad_arguments(lib):
     assert lib.lib.ck_oz_split(x.data_ptr(), 48, 128, 48, buf.data_ptr(), None, sc.data_ptr(), _stream()) == lib.CK_ERR_ARG  # k % 32
     assert lib.lib.ck_oz_split(x.data_ptr(), 48, 128, 32, None, None, sc.data_ptr(), _stream()) == lib.CK_ERR_ARG          # no output
     assert lib.lib.ck_oz_gemm(buf.data_ptr(), sc.data_ptr(), 128, buf.data_ptr(), sc.data_ptr(), 64, 32, x.data_ptr(), 32, 0,
-                              _stream()) == lib.CK_ERR_ARG                                                                   # ldc < n
+                              0, _stream()) == lib.CK_ERR_ARG                                                                   # ldc < n
 
 
 def _spd(n, seed, nugget=0.01):

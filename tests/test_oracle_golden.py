@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 import cokrig_oracle as orc
-from conftest import golden, relerr
+from conftest import GOLDEN, golden, relerr
 
 
 def test_matern_correlation_and_scaling():
@@ -145,3 +145,23 @@ def test_closed_form_loocv_matches_reference_loop():
     p_cf = z[k] - (sinv @ z)[k] / np.diagonal(sinv)[k]
     s_cf = 1 / np.sqrt(np.diagonal(sinv)[k])
     assert relerr(p_cf, p_loop) < 1e-9 and relerr(s_cf, s_loop) < 1e-10
+
+
+def test_oracle_at_baseline_c1_size_vs_reference_fixture():
+    """The oracle at BASELINE config C1's real size (N = 3 200, k = 142..390 neighbours per target) against outputs of the
+    unmodified reference (tests/golden/make_golden_r2.py): point cokriging on a 40-target subset and the joint solve."""
+    import sys
+    sys.path.insert(0, GOLDEN)
+    from make_golden_r2 import C1_PARAMS, inputs_c1
+    g = golden("at_size_c1")
+    grid, pc = inputs_c1()
+    P = orc.Params(C1_PARAMS)
+    z = [g["z0_t01"], g["z1_t01"]]
+    pr, sd, k, _ = orc.point_predict(P, 1, [grid, grid], z, pc[:40], 0.2, "euclidean")
+    np.testing.assert_array_equal(k, g["point_k_t01"][:40])
+    assert relerr(pr, g["point_pred_t01"][:40]) < 1e-13 and np.abs(sd - g["point_sd_t01"][:40]).max() < 1e-13
+    cm, low, zs = orc.sim_fields(P, grid, seed=1)  # the simulated fields themselves (src/sim.py:33-65)
+    np.testing.assert_allclose(zs[0], z[0], rtol=0, atol=1e-11)
+    pj, ej, _ = orc.joint_predict(P, 1, [grid, grid], z, pc[:50], "euclidean")
+    assert relerr(pj, g["joint_pred_t01"][:50]) < 1e-10
+    assert np.abs(ej ** 2 - np.maximum(g["joint_var_t01"][:50], 0)).max() < 1e-12

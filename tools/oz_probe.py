@@ -61,7 +61,7 @@ def oz_gemm(a, b, c, lower=False):
     fa, _, sa = split(a, True, False)
     _, fb, sb = split(b, False, True)
     _lib.check(lib.ck_oz_gemm(fa.data_ptr(), sa.data_ptr(), a.shape[0], fb.data_ptr(), sb.data_ptr(), b.shape[0], a.shape[1],
-                              c.data_ptr(), c.stride(0), 1 if lower else 0, stream()), "ck_oz_gemm")
+                              c.data_ptr(), c.stride(0), 1 if lower else 0, 0, stream()), "ck_oz_gemm")
     torch.cuda.synchronize()
 
 
@@ -157,7 +157,7 @@ def perf(out, sizes):
             else:
                 sb = sa
             for _ in range(2):
-                lib.ck_oz_gemm(fa.data_ptr(), sa.data_ptr(), m, fb.data_ptr(), sb.data_ptr(), n, k, c.data_ptr(), c.stride(0), int(lower), stream())
+                lib.ck_oz_gemm(fa.data_ptr(), sa.data_ptr(), m, fb.data_ptr(), sb.data_ptr(), n, k, c.data_ptr(), c.stride(0), int(lower), 0, stream())
             torch.cuda.synchronize()
             reps = 5
             e0.record()
@@ -165,7 +165,7 @@ def perf(out, sizes):
                 lib.ck_oz_split(a.data_ptr(), a.stride(0), m, k, fa.data_ptr(), fb.data_ptr() if lower else None, sa.data_ptr(), stream())
             e1.record()
             for _ in range(reps):
-                lib.ck_oz_gemm(fa.data_ptr(), sa.data_ptr(), m, fb.data_ptr(), sb.data_ptr(), n, k, c.data_ptr(), c.stride(0), int(lower), stream())
+                lib.ck_oz_gemm(fa.data_ptr(), sa.data_ptr(), m, fb.data_ptr(), sb.data_ptr(), n, k, c.data_ptr(), c.stride(0), int(lower), 0, stream())
             e2.record()
             torch.cuda.synchronize()
             t_split, t_gemm = e0.elapsed_time(e1) / reps, e1.elapsed_time(e2) / reps
@@ -180,7 +180,7 @@ def perf(out, sizes):
             torch.cuda.synchronize()
             dbg = torch.zeros(8 * 148, dtype=torch.int64, device="cuda")
             lib.ck_oz_debug_buffer(dbg.data_ptr())
-            lib.ck_oz_gemm(fa.data_ptr(), sa.data_ptr(), m, fb.data_ptr(), sb.data_ptr(), n, k, c.data_ptr(), c.stride(0), int(lower), stream())
+            lib.ck_oz_gemm(fa.data_ptr(), sa.data_ptr(), m, fb.data_ptr(), sb.data_ptr(), n, k, c.data_ptr(), c.stride(0), int(lower), 0, stream())
             torch.cuda.synchronize()
             lib.ck_oz_debug_buffer(None)
             d = dbg.cpu().numpy().reshape(148, 8).astype(float)
