@@ -223,12 +223,22 @@ int ck_local_count(const double* xy0_dev, ck_i64 n0, const double* xy1_dev, ck_i
  * params_sigma: the model the local covariance MATRIX is built from (the reference freezes Sigma when the Predictor is
  * constructed, src/point_prediction.py:42); params_pred (NULL = params_sigma): the model of the target-to-neighbour
  * VECTOR, evaluated at call time (src/point_prediction.py:115-125); c0 = covariance(i, 0, use_nugget=True) as the caller
- * computed it (src/point_prediction.py:66).  kmax = max_c k_dev[c]; k_dev / seg_dev from pass 1. */
+ * computed it (src/point_prediction.py:66).  kmax = max_c k_dev[c]; k_dev / seg_dev from pass 1.
+ * sigma_dev (optional, NULL = off): the joint covariance of the stacked data as ck_joint_cov writes it ((n0 + n1)^2, row-major,
+ * leading dimension ld_sigma) -- the device counterpart of the reference's stored Predictor.Sigma (src/point_prediction.py:98-113).
+ * When given, the entries of every local matrix are GATHERED from it (src/point_prediction.py:159-179 does the same with
+ * np.ix_) instead of being re-computed from the coordinates: faster, at the price of N^2 memory. */
 int ck_local_predict(const double* xy0_dev, const double* z0_dev, ck_i64 n0, const double* xy1_dev, const double* z1_dev,
                      ck_i64 n1, const double* xyp_dev, ck_i64 m, const double* params_sigma /*HOST*/,
                      const double* params_pred /*HOST or NULL*/, int n_procs, int i_pred, int metric, double max_dist, int cv,
-                     double c0, const int* k_dev, const int* seg_dev, ck_i64 kmax, double* pred_dev, double* sd_dev,
-                     int* info_dev, void* ws_dev, void* stream);
+                     double c0, const double* sigma_dev, ck_i64 ld_sigma, const int* k_dev, const int* seg_dev, ck_i64 kmax,
+                     double* pred_dev, double* sd_dev, int* info_dev, void* ws_dev, void* stream);
+
+/* Profiling aid: when set to a device buffer of 6 int64 counters, every following ck_local_predict launch adds the
+ * cycles thread 0 of each CTA spent in [0] neighbour scan, [1] covariance entries, [2] DMMA main loops, [3] diagonal
+ * blocks, [4] panel products + stores, [5] the final reductions.  NULL switches it off (default).  Only a
+ * -DCK_LOCAL_PROFILE build carries the counters; the product build returns CK_ERR_UNSUPPORTED for a non-NULL buffer. */
+int ck_local_debug_buffer(void* dev_counters);
 
 /* ------------------------------------------------------------------------------------------------
  * Multi-GPU building blocks (one process per GPU; the collectives are NCCL broadcasts issued by the host

@@ -35,15 +35,19 @@ def _deps_mtime() -> float:
     return max(os.path.getmtime(f) for f in files)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= _deps_mtime():
-        return OUT
+def build(force: bool = False, verbose: bool = False, variant: str = "", defines=()) -> str:
+    """variant / defines: a tuning or profiling build next to the product library (tools only), e.g.
+    build(variant="prof", defines=("CK_LOCAL_PROFILE",)) -> cokrig_b200/libvariant_prof.so, selected at run time with
+    COKRIG_B200_LIB=<path>."""
+    out = OUT if not variant else os.path.join(HERE, "cokrig_b200", f"libvariant_{variant}.so")
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= _deps_mtime():
+        return out
     os.makedirs(OBJ, exist_ok=True)
     nvcc = _nvcc()
 
     def compile_one(src):
-        obj = os.path.join(OBJ, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(OBJ, src.replace(".cu", (f"_{variant}" if variant else "") + ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log = r.stdout + r.stderr
         with open(obj + ".log", "w") as f:
@@ -58,12 +62,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
         objs = list(ex.map(compile_one, SOURCES))
     # --cudart shared: the CUDA runtime is NOT embedded in the product binary (it resolves to the libcudart.so.12 that
     # torch has already loaded, so the library and torch share one runtime instance)
-    cmd = [nvcc, "-shared", "--cudart", "shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT, *objs]
+    cmd = [nvcc, "-shared", "--cudart", "shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out, *objs]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = tuple(a[2:] for a in sys.argv[1:] if a.startswith("-D"))
+    var = next((a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--variant=")), "")
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, variant=var, defines=defs))

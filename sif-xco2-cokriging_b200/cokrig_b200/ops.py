@@ -337,14 +337,17 @@ def vario_bin(Xa: torch.Tensor, va: torch.Tensor, mean_a: float, Xb: torch.Tenso
 # ------------------------------------------------------------------------------------------------ K4
 def local_predict(coords: Sequence[torch.Tensor], values: Sequence[torch.Tensor], pcoords: torch.Tensor, params,
                   n_procs: int, i_pred: int, metric: int, max_dist: float, cv: bool = False, params_pred=None,
-                  c0: Optional[float] = None):
+                  c0: Optional[float] = None, sigma: Optional[torch.Tensor] = None):
     """Batched local-neighbourhood cokriging: returns (pred, sd, k, info) numpy arrays over targets
     (src/point_prediction.py:127-249).  info: 0 ok, >0 local matrix not PD (pred = sd = NaN),
     -1 valid prediction but the augmented matrix is not PD (the reference only warns).
 
     params: the model of the local covariance matrix (the reference freezes it at construction);
     params_pred: the model of the target-to-neighbour vector (default: params); c0: the target variance
-    the caller computed (default: sigma_i^2 + nugget_i of params_pred)."""
+    the caller computed (default: sigma_i^2 + nugget_i of params_pred).
+    sigma: optional joint covariance of the stacked data on the device (``joint_cov(coords, params, ...)``, the
+    counterpart of the reference's stored ``Predictor.Sigma``): local matrices are then gathered from it
+    instead of being re-computed from the coordinates (faster; needs N^2 memory)."""
     dev = require_cuda()
     pv, pp = _params(params, n_procs)
     qv, qp = _params(params if params_pred is None else params_pred, n_procs)
@@ -366,6 +369,8 @@ def local_predict(coords: Sequence[torch.Tensor], values: Sequence[torch.Tensor]
     sd = torch.empty(max(m, 1), dtype=F64, device=dev)
     info = torch.zeros(max(m, 1), dtype=torch.int32, device=dev)
     check(lib.ck_local_predict(_ptr(coords[0]), _ptr(values[0]), n0, _ptr(c1), _ptr(z1), n1, _ptr(pcoords), m, pp, qp,
-                               n_procs, i_pred, metric, float(max_dist), int(cv), float(c0), _ptr(k), _ptr(seg), kmax,
+                               n_procs, i_pred, metric, float(max_dist), int(cv), float(c0), _ptr(sigma),
+                               0 if sigma is None else (sigma.stride(0) if sigma.shape[0] > 1 else max(sigma.shape[1], 1)),
+                               _ptr(k), _ptr(seg), kmax,
                                _ptr(pred), _ptr(sd), _ptr(info), _ptr(ws), _stream()), "ck_local_predict")
     return (pred[:m].cpu().numpy(), sd[:m].cpu().numpy(), k[:m].cpu().numpy(), info[:m].cpu().numpy())

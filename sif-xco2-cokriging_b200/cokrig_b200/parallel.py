@@ -40,8 +40,10 @@ def grid_shape(world: int) -> Tuple[int, int]:
 
 
 class ProcessGrid:
-    """rank = p * Q + q.  Column groups (fixed q) carry the diagonal-tile broadcast; panel broadcasts use
-    the world group."""
+    """rank = p * Q + q.  Column groups (fixed q: the P ranks of one process column) carry the diagonal-tile
+    broadcast and the exchange of the panel tiles that become B operands; row groups (fixed p: the Q ranks of one
+    process row) carry the panel broadcast.  A rank therefore receives only the panel rows of its own process row
+    and the panel tiles of its own tile columns -- what ScaLAPACK does with row / column communicators."""
 
     def __init__(self, P: Optional[int] = None, Q: Optional[int] = None):
         self.world = dist.get_world_size() if dist.is_initialized() else 1
@@ -53,9 +55,13 @@ class ProcessGrid:
         self.P, self.Q = P, Q
         self.p, self.q = divmod(self.rank, Q)
         self.col_groups = [None] * Q
+        self.row_groups = [None] * P
         if self.world > 1 and P > 1:
             for qq in range(Q):  # every rank must create every group, in the same order
                 self.col_groups[qq] = dist.new_group([pp * Q + qq for pp in range(P)])
+        if self.world > 1 and Q > 1:
+            for pp in range(P):
+                self.row_groups[pp] = dist.new_group([pp * Q + qq for qq in range(Q)])
 
     def rank_of(self, p: int, q: int) -> int:
         return p * self.Q + q
@@ -305,8 +311,11 @@ class BlockCyclicCokriging:
 
     Layout: see csrc/ck_mg.cu.  Per tile column k (right-looking):
         diagonal owner      potrf(tile k,k)                                  -> broadcast down process column k%Q
-        process column k%Q  panel rows I>k:  A_Ik <- A_Ik L_kk^-T (TRSM)     -> broadcast to every rank
-        every rank          A_IJ -= L_Ik L_Jk^T on its tiles I>k, J>k, J<=I  (one DMMA launch, ck_mg_update)
+        process column k%Q  panel rows I>k:  A_Ik <- A_Ik L_kk^-T (TRSM)     -> broadcast along each process ROW (a rank gets
+                                                                                only the tiles I = p mod P: its A operand)
+        every rank          panel tiles J = q mod Q (its B operand)          <- all-gather inside its process COLUMN of the
+                                                                                tiles each member holds after the row broadcast
+        every rank          A_IJ -= L_Ik L_Jk^T on its tiles I>k, J>k, J<=I  (one launch: ck_oz_mg_update / ck_mg_update)
     with one-panel look-ahead: the owners of column k+1 update that column first, factor it and start its
     broadcasts on a high-priority stream while everybody's trailing update of step k is still running.
     The target rows (C^T and z) ride along as extra row tiles, so after the sweep they hold L^-1 c and
@@ -346,11 +355,27 @@ class BlockCyclicCokriging:
     def solve(self, coords: Sequence, z, targets, params, n_procs: int, i_pred: int, metric: int):
         """coords / z / targets: host arrays replicated on every rank.  Returns (pred, var, info) as numpy
         arrays / int, identical on every rank; info > 0 = order of the first non-PD leading minor."""
-        K, g, tb = self.k, self.g, self.tb
-        params = np.asarray(params, dtype=np.float64)
+        K = self.k
         coords_d = [K.to_device(np.ascontiguousarray(np.asarray(c, dtype=np.float64))) for c in coords[:n_procs]]
         z_d = K.to_device(np.ascontiguousarray(np.hstack([np.asarray(v, dtype=np.float64) for v in z[:n_procs]])))
         t_d = K.to_device(np.ascontiguousarray(np.asarray(targets, dtype=np.float64)))
+        pred_d, var_d, info = self.solve_device(coords_d, z_d, t_d, params, n_procs, i_pred, metric)
+        K.sync()
+        pred, var = pred_d.cpu().numpy(), var_d.cpu().numpy()
+        inf = info.cpu().numpy()
+        TC, tb = self.TC, self.tb
+        bad = np.nonzero(inf[:TC] > 0)[0]
+        first_bad = int(bad[0] * tb + inf[bad[0]]) if bad.size else 0
+        if first_bad > self.N:
+            first_bad = 0  # cannot happen: the pad is the identity
+        self.timings = self._elapsed(self._ev)
+        return pred, var, first_bad
+
+    def solve_device(self, coords_d: Sequence, z_d, t_d, params, n_procs: int, i_pred: int, metric: int):
+        """The sweep on device-resident inputs (replicated on every rank): returns (pred, var, info) as device tensors
+        (m,), (m,), (tile columns,) without synchronising the host -- info[k] > 0 flags tile column k."""
+        K, g, tb = self.k, self.g, self.tb
+        params = np.asarray(params, dtype=np.float64)
         N, m = int(z_d.shape[0]), int(t_d.shape[0])
         self._layout(N, m)
         P, Q, p, q = g.P, g.Q, g.p, g.q
@@ -360,8 +385,11 @@ class BlockCyclicCokriging:
         c0 = sig * sig + nug
 
         local = K.empty(max(LRt * tb, 1), max(LCt * tb, 1))
-        stage = K.empty(2, P, max(self.LRmax, 1), tb, tb)          # double-buffered gathered panel
-        bgather = K.empty(max(LCt, 1), tb, tb)                      # B operand: panel tiles of my tile columns
+        stage = K.empty(2, max(self.LRmax, 1), tb, tb)             # double-buffered: panel tiles of my process row (A operand)
+        bcols = K.empty(2, max(LCt, 1), tb, tb)                     # double-buffered: panel tiles of my tile columns (B operand)
+        cmax = (max(LCt, 1) + P - 1) // P + 1
+        self._xsend = K.empty(cmax, tb, tb) if P > 1 else None      # column exchange: my contribution / everybody's
+        self._xrecv = K.empty(P, cmax, tb, tb) if P > 1 else None
         packs = [K.empty(K.pack_size(tb)) for _ in range(2)]
         info = K.zeros(max(TC, 1), dtype=torch.int32)
         ev = {"t0": self._mark()}
@@ -370,22 +398,22 @@ class BlockCyclicCokriging:
         with K.stream("main"):
             assembled = K.event()  # the panel stream must not touch `local` before the assembly kernels are done
 
-        main_done = [None, None]  # main_done[b]: last trailing update that read stage[b] has finished
-        panel_ready = self._factor_panel(0, local, stage[0], packs[0], info, None, assembled) if TC else None
+        main_done = [None, None]  # main_done[b]: last trailing update that read stage[b] / bcols[b] has finished
+        panel_ready = self._factor_panel(0, local, stage[0], bcols[0], packs[0], info, None, assembled) if TC else None
         for k in range(TC):
             buf = k % 2
             nxt = None
             if self.lookahead and k + 1 < TC:
                 # column k+1 first (its owners), then its panel, all on the panel stream
-                nxt = self._factor_panel(k + 1, local, stage[1 - buf], packs[1 - buf], info,
-                                         (k, stage[buf], panel_ready), main_done[1 - buf])
+                nxt = self._factor_panel(k + 1, local, stage[1 - buf], bcols[1 - buf], packs[1 - buf], info,
+                                         (k, stage[buf], bcols[buf], panel_ready), main_done[1 - buf])
             with K.stream("main"):
                 K.wait(panel_ready)
                 skip = (k + 1) if (self.lookahead and k + 1 < TC) else None
-                self._trailing_update(k, local, stage[buf], bgather, skip_col=skip)
+                self._trailing_update(k, local, stage[buf], bcols[buf], skip_col=skip)
                 main_done[buf] = K.event()
             if not self.lookahead and k + 1 < TC:
-                nxt = self._factor_panel(k + 1, local, stage[1 - buf], packs[1 - buf], info, None, main_done[buf])
+                nxt = self._factor_panel(k + 1, local, stage[1 - buf], bcols[1 - buf], packs[1 - buf], info, None, main_done[buf])
             panel_ready = nxt
         ev["t2"] = self._mark()
 
@@ -412,18 +440,12 @@ class BlockCyclicCokriging:
                     total += allp[r]
             else:
                 total = part
+            pred = total[0, :m]
+            var = c0 - total[1, :m]
         ev["t3"] = self._mark()
-        K.sync()
-        pred = total[0, :m].cpu().numpy()
-        var = c0 - total[1, :m].cpu().numpy()
-        inf = info.cpu().numpy()
-        bad = np.nonzero(inf[:TC] > 0)[0]
-        first_bad = int(bad[0] * tb + inf[bad[0]]) if bad.size else 0
-        if first_bad > N:
-            first_bad = 0  # cannot happen: the pad is the identity
-        self.timings = self._elapsed(ev)
+        self._ev = ev
         self._keep = (local, stage)  # factor stays resident (logdet / diagnostics)
-        return pred, var, first_bad
+        return pred, var, info
 
     def logdet(self) -> float:
         """2 sum log L_kk over the diagonal tiles (after solve()), summed over ranks."""
@@ -464,10 +486,10 @@ class BlockCyclicCokriging:
         return out[:, : self.N].cpu().numpy()
 
     # -- pieces -----------------------------------------------------------------------------------
-    def _factor_panel(self, k: int, local, stage_b, pack, info, pending, stage_free):
-        """Panel stream: [apply `pending` = (k-1, its stage, its ready event) to column k on its owners] ->
-        potrf(k,k) -> broadcast -> TRSM of the rows below -> gather the panel on every rank.
-        Returns the event after which stage_b holds panel k everywhere."""
+    def _factor_panel(self, k: int, local, stage_b, bcols_b, pack, info, pending, stage_free):
+        """Panel stream: [apply `pending` = (k-1, its stage, its column tiles, its ready event) to column k on its owners]
+        -> potrf(k,k) -> broadcast down the process column -> TRSM of the rows below -> row broadcast -> column exchange.
+        Returns the event after which stage_b / bcols_b hold this rank's share of panel k."""
         K, g, tb = self.k, self.g, self.tb
         P, Q, p, q = g.P, g.Q, g.p, g.q
         qk, pk = k % Q, k % P
@@ -475,33 +497,53 @@ class BlockCyclicCokriging:
         with K.stream("panel"):
             K.wait(stage_free)
             if pending is not None:
-                kp, stage_prev, ready_prev = pending
+                kp, stage_prev, bcols_prev, ready_prev = pending
                 K.wait(ready_prev)
                 if q == qk:  # bring column k up to date with panel k-1 (rows I >= k)
                     li0 = first_local_after(k - 1, P, p)
                     if li0 < self.LRt:
-                        A = stage_prev[p, li0: self.LRt].view(-1, tb)
-                        B = stage_prev[k % P, k // P]
+                        A = stage_prev[li0: self.LRt].view(-1, tb)
+                        B = bcols_prev[ljk]  # tile k of panel k-1: column k is one of my tile columns
                         C = local[li0 * tb: self.LRt * tb, ljk * tb:(ljk + 1) * tb]
                         K.update(A, B, C, tb, li0 * P + p, P, k, Q)
+            l0 = first_local_after(k, P, p)
             if q == qk:
                 if p == pk:
                     lik = k // P
                     K.potrf_tile(local[lik * tb:(lik + 1) * tb, ljk * tb:(ljk + 1) * tb], pack, info[k: k + 1])
                 if P > 1:
                     dist.broadcast(pack, src=g.rank_of(pk, qk), group=g.col_groups[qk])
-                li0 = first_local_after(k, P, p)
-                if li0 < self.LRt:
-                    rows = local[li0 * tb: self.LRt * tb, ljk * tb:(ljk + 1) * tb]
-                    K.trsm(pack, tb, rows, stage_b[p, li0: self.LRt].view(-1, tb))
-            if g.world > 1:
-                for pp in range(P):
-                    l0, l1 = first_local_after(k, P, pp), local_tiles(self.TR, P, pp)
-                    if l0 < l1:
-                        dist.broadcast(stage_b[pp, l0:l1], src=g.rank_of(pp, qk))
+                if l0 < self.LRt:
+                    rows = local[l0 * tb: self.LRt * tb, ljk * tb:(ljk + 1) * tb]
+                    K.trsm(pack, tb, rows, stage_b[l0: self.LRt].view(-1, tb))
+            # A operand: the panel tiles of my process row, from the member of my row that owns tile column k
+            if Q > 1 and l0 < self.LRt:
+                dist.broadcast(stage_b[l0: self.LRt], src=g.rank_of(p, qk), group=g.row_groups[p])
+            # B operand: the panel tiles J of my tile columns (J > k); tile J sits with process row J mod P after the row
+            # broadcast, so the members of my process column all-gather their shares
+            lj0 = first_local_after(k, Q, q)
+            if lj0 < self.LCt:
+                Js = [lj * Q + q for lj in range(lj0, self.LCt)]
+                if P == 1:
+                    bcols_b[lj0: self.LCt].copy_(stage_b[Js[0]: Js[-1] + 1: Q])
+                else:
+                    share = [[J for J in Js if J % P == pp] for pp in range(P)]
+                    cnt = max(len(sh) for sh in share)
+                    send, recv = self._xsend[:cnt], self._xrecv[:, :cnt]
+                    mine = share[p]
+                    send = self._xsend[:cnt]                           # my share, padded to the largest share
+                    recv = self._xrecv.view(-1, tb, tb)[: P * cnt]      # [member of my process column][tile]
+                    mine = share[p]
+                    if mine:
+                        idx = torch.tensor([J // P for J in mine], dtype=torch.int64, device=stage_b.device)
+                        torch.index_select(stage_b, 0, idx, out=send[: len(mine)])
+                    dist.all_gather_into_tensor(recv.view(-1), send.view(-1), group=g.col_groups[q])
+                    where = {J: pp * cnt + i for pp in range(P) for i, J in enumerate(share[pp])}
+                    sel = torch.tensor([where[J] for J in Js], dtype=torch.int64, device=stage_b.device)
+                    torch.index_select(recv, 0, sel, out=bcols_b[lj0: self.LCt])
             return K.event()
 
-    def _trailing_update(self, k: int, local, stage_b, bgather, skip_col=None) -> None:
+    def _trailing_update(self, k: int, local, stage_b, bcols_b, skip_col=None) -> None:
         """A_IJ -= L_Ik L_Jk^T on my tiles with I > k, J > k (J <= I), minus column `skip_col` (done by look-ahead)."""
         K, g, tb = self.k, self.g, self.tb
         P, Q, p, q = g.P, g.Q, g.p, g.q
@@ -511,19 +553,8 @@ class BlockCyclicCokriging:
             lj0 += 1
         if li0 >= self.LRt or lj0 >= self.LCt:
             return
-        # my rows can only see columns J <= I_max; extra (target) tiles see all of them
-        A = stage_b[p, li0: self.LRt].view(-1, tb)
-        nb = self.LCt - lj0
-        idx_p = [(lj * Q + q) % P for lj in range(lj0, self.LCt)]
-        idx_t = [(lj * Q + q) // P for lj in range(lj0, self.LCt)]
-        if P == 1 and Q == 1:
-            B = stage_b[0, idx_t[0]: idx_t[0] + nb].view(-1, tb)
-        else:
-            flat = stage_b.view(P * stage_b.shape[1], tb, tb)
-            sel = torch.tensor([a * stage_b.shape[1] + b for a, b in zip(idx_p, idx_t)], dtype=torch.int64,
-                               device=stage_b.device)
-            torch.index_select(flat, 0, sel, out=bgather[:nb])
-            B = bgather[:nb].view(-1, tb)
+        A = stage_b[li0: self.LRt].view(-1, tb)
+        B = bcols_b[lj0: self.LCt].view(-1, tb)
         C = local[li0 * tb: self.LRt * tb, lj0 * tb: self.LCt * tb]
         K.update(A, B, C, tb, li0 * P + p, P, lj0 * Q + q, Q)
 

@@ -37,13 +37,21 @@ constexpr int LP = 32;             // block-column (panel) width
 constexpr int LTM = 64;            // rows per tile
 constexpr int LK = 16;             // k-depth per pipeline stage
 constexpr int LLD = LK + 4;        // staging row stride (doubles): % 16 == 4 -> conflict-free DMMA fragment loads
-constexpr int LSTG = 2;            // pipeline stages
+#ifndef CK_LOCAL_STAGES
+#define CK_LOCAL_STAGES 2
+#endif
+constexpr int LSTG = CK_LOCAL_STAGES;  // pipeline stages
 constexpr int LWLD = LP + 4;       // row stride of the W tile and of X_d
 constexpr int L_THREADS = 128;
 constexpr int L_WARPS = L_THREADS / 32;
 constexpr int L_STAGE_ELEMS = (LTM + LP) * LLD;
 constexpr int L_SMEM_KMAX = 2048;  // neighbour records live in shared memory up to this k, in the workspace beyond
-constexpr int L_FAST_NONE = -1;
+constexpr int L_FAST_NONE = -1;    // FAST template values: 0..3 closed-form nu (polynomial path), -1 generic, -2 gather
+constexpr int L_GATHER = -2;
+#ifndef CK_LOCAL_MIN_CTAS
+#define CK_LOCAL_MIN_CTAS 4
+#endif
+constexpr int L_MIN_CTAS = CK_LOCAL_MIN_CTAS;  // CTAs per SM the register allocation is bounded for
 static_assert(LTM * LWLD <= LSTG * L_STAGE_ELEMS, "the W tile aliases the staging buffers");
 
 struct LocalArgs {
@@ -53,12 +61,14 @@ struct LocalArgs {
   CkMatern C[2];    // target-to-process-j blocks for the predicted process (own block carries the nugget)
   int n_procs, i_pred, metric, cv;
   double max_dist, c0;
+  const double* sigma; long long ld_sigma;  // optional precomputed joint covariance (gather mode)
   const int* kcount; const int* kseg; long long kmax, kmaxp;
   double* pred; double* sd; int* info;
   double* ws;       // slots x [(kmaxp + 2) x kmaxp factor rows | optional neighbour records]
   long long slot_stride;
   int pts_in_ws;
   unsigned int* counter;
+  long long* dbg;   // optional phase cycle counters (ck_local_debug_buffer): scan, init, main loop, diagonal block, panel, rest
 };
 
 // out-of-line so that the five Matern variants are instantiated once per kernel, not per call site
@@ -134,7 +144,7 @@ __device__ __forceinline__ long long local_seglen(long long n) { return ((n + L_
 
 // One warp scans its segment of process `proc` in index order.  STORE: kept points are appended at `off` (warp-private,
 // ordered); returns the number kept.
-template <int METRIC, bool STORE>
+template <int METRIC, bool STORE, bool GATHER>
 __device__ __forceinline__ int local_scan_segment(const LocalArgs& g, const LocalFilter& f, const CkPoint& p0, int proc, int warp,
                                                   int lane, int off, double* pa, double* pb, double* pc, double* pcv, double* pzv) {
   const long long n = g.n[proc], sl = local_seglen(n);
@@ -158,9 +168,13 @@ __device__ __forceinline__ int local_scan_segment(const LocalArgs& g, const Loca
     const unsigned mask = __ballot_sync(0xffffffffu, keep);
     if (STORE && keep) {
       const int pos = off + cnt + __popc(mask & ((1u << lane) - 1u));
-      pa[pos] = q.a;
-      pb[pos] = q.b;
-      if (METRIC == CK_METRIC_HAVERSINE) pc[pos] = q.c;
+      if (GATHER) {
+        reinterpret_cast<int*>(pa)[pos] = (int)(proc ? g.n[0] + i : i);  // row / column of the joint matrix
+      } else {
+        pa[pos] = q.a;
+        pb[pos] = q.b;
+        if (METRIC == CK_METRIC_HAVERSINE) pc[pos] = q.c;
+      }
       pcv[pos] = cov_dyn(g.C[proc], d);
       pzv[pos] = g.z[proc][i];
     }
@@ -180,7 +194,7 @@ __global__ void __launch_bounds__(L_THREADS) ck_local_count_kernel(const __grid_
     for (int proc = 0; proc < 2; ++proc) {
       int cnt = 0;
       if (proc < g.n_procs)
-        cnt = local_scan_segment<METRIC, false>(g, f, p0, proc, warp, lane, 0, nullptr, nullptr, nullptr, nullptr, nullptr);
+        cnt = local_scan_segment<METRIC, false, false>(g, f, p0, proc, warp, lane, 0, nullptr, nullptr, nullptr, nullptr, nullptr);
       if (lane == 0) seg[proc * L_WARPS + warp] = cnt;
     }
     __syncthreads();
@@ -201,6 +215,10 @@ __global__ void __launch_bounds__(L_THREADS) ck_local_count_kernel(const __grid_
 template <int METRIC, int FAST>
 __device__ __forceinline__ double local_cov_entry(const LocalArgs& g, int i, int j, int k0, const double* pa, const double* pb,
                                                   const double* pc) {
+  if (FAST == L_GATHER) {  // j <= i in the local order implies column <= row in the joint matrix: the lower triangle
+    const int* gi = reinterpret_cast<const int*>(pa);
+    return __ldg(g.sigma + (long long)gi[i] * g.ld_sigma + gi[j]);
+  }
   CkPoint pi, pj;
   pi.a = pa[i]; pi.b = pb[i];
   pj.a = pa[j]; pj.b = pb[j];
@@ -209,7 +227,7 @@ __device__ __forceinline__ double local_cov_entry(const LocalArgs& g, int i, int
   // j <= i and process 0 comes first: (proc_j, proc_i) in {(0,0), (0,1), (1,1)}; rows of the reference block come from
   // the lower process id (src/point_prediction.py:159-179)
   const int blk = (i < k0) ? 0 : (j < k0 ? 1 : 2);
-  if (FAST != L_FAST_NONE) return ck_matern_cov_fast<FAST>(g.S[blk], ck_dist_fast<METRIC>(pj, pi));
+  if (FAST >= 0) return ck_matern_cov_fast<(FAST >= 0 ? FAST : 0)>(g.S[blk], ck_dist_fast<METRIC>(pj, pi));
   return cov_dyn(g.S[blk], ck_dist<METRIC>(pj, pi));
 }
 
@@ -225,8 +243,60 @@ __device__ __forceinline__ double local_entry(const LocalArgs& g, int i, int j, 
   return (i == kp) ? pcv[j] : ((i == kp + 1) ? pzv[j] : 0.0);
 }
 
+// 32 x 32 diagonal block (one warp; out of line so that its 64 + 64 registers of row / column state are allocated
+// separately from the tile code): Wt rows 0..31 hold the lower triangle of D on entry and L_d on exit (D = L_d L_d^T), Xd
+// receives X_d = L_d^-1 (explicit zeros above the diagonal).  Returns 0 or 1 + the first column whose pivot is not > 0.
+static __device__ __noinline__ int local_diag_block(double* Wt, double* Xd, double* rsd, int lane) {
+  // ---- elimination, lane = row; a[kk] holds the UNSCALED column entry until column kk is finished: only 1 / d sits on
+  // the pivot chain (approximate reciprocal + two Newton steps), the 32 square roots are taken after the loop
+  double a[LP];
+#pragma unroll
+  for (int kk = 0; kk < LP; ++kk) a[kk] = Wt[lane * LWLD + kk];
+  int first_bad = 0;
+  double dk = 1.0;
+#pragma unroll
+  for (int kk = 0; kk < LP; ++kk) {
+    const double d = __shfl_sync(0xffffffffu, a[kk], kk);
+    if (!(d > 0.0) && first_bad == 0) first_bad = kk + 1;
+    if (lane == kk) dk = d;
+    double invd;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(invd) : "d"(d));
+    invd = fma(fma(-d, invd, 1.0), invd, invd);
+    invd = fma(fma(-d, invd, 1.0), invd, invd);
+    const double u = a[kk];
+    const double w = u * invd;
+#pragma unroll
+    for (int jj = kk + 1; jj < LP; ++jj) {
+      const double ujk = __shfl_sync(0xffffffffu, u, jj);
+      a[jj] = fma(-w, ujk, a[jj]);
+    }
+  }
+  const double sqv = sqrt(dk);
+  const double rsv = 1.0 / sqv;
+  rsd[lane] = rsv;
+#pragma unroll
+  for (int kk = 0; kk < LP; ++kk) {
+    const double rs = __shfl_sync(0xffffffffu, rsv, kk);
+    if (kk <= lane) Wt[lane * LWLD + kk] = (lane == kk) ? sqv : a[kk] * rs;
+  }
+  __syncwarp();
+  // ---- X_d = L_d^-1, lane = column: forward substitution on e_lane, L_d read by broadcast
+  double x[LP];
+#pragma unroll
+  for (int i = 0; i < LP; ++i) x[i] = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+  for (int kk = 0; kk < LP; ++kk) {
+    x[kk] *= rsd[kk];
+#pragma unroll
+    for (int i = kk + 1; i < LP; ++i) x[i] = fma(-Wt[i * LWLD + kk], x[kk], x[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < LP; ++i) Xd[i * LWLD + lane] = x[i];
+  return first_bad;
+}
+
 template <int METRIC, int FAST>
-__global__ void __launch_bounds__(L_THREADS, 4) ck_local_predict_kernel(const __grid_constant__ LocalArgs g) {
+__global__ void __launch_bounds__(L_THREADS, L_MIN_CTAS) ck_local_predict_kernel(const __grid_constant__ LocalArgs g) {
   extern __shared__ __align__(16) double lsm[];
   double* stage = lsm;                                  // LSTG x (LTM + LP) x LLD; aliased by the W tile
   double* Wt = lsm;                                     // LTM x LWLD
@@ -241,9 +311,25 @@ __global__ void __launch_bounds__(L_THREADS, 4) ck_local_predict_kernel(const __
   const long long ld = g.kmaxp;
   const long long kcap = (g.kmax + 7) / 8 * 8;
   double* pbase = g.pts_in_ws ? Lw + (size_t)(g.kmaxp + 2) * (size_t)g.kmaxp : pts_sm;
-  double *pa = pbase, *pb = pa + kcap, *pcv = pb + kcap, *pzv = pcv + kcap, *pc = pzv + kcap;
+  // records: [a | b | c-vector | z | cos(lat)]; gather mode: [joint index (int32) | c-vector | z]
+  double *pa = pbase, *pb = pa + kcap, *pcv = (FAST == L_GATHER) ? pa + kcap / 2 : pb + kcap, *pzv = pcv + kcap, *pc = pzv + kcap;
   const double qnan = __longlong_as_double(0x7FF8000000000000LL);
   const unsigned sbase = (unsigned)__cvta_generic_to_shared(stage);
+#ifdef CK_LOCAL_PROFILE  // phase counters (tools/k4_run.py --phases on a -DCK_LOCAL_PROFILE build); off in the product build
+  long long tph[6] = {0, 0, 0, 0, 0, 0}, tlast = 0;
+  const bool prof = g.dbg != nullptr && tid == 0;
+#define L_STAMP(i)                      \
+  do {                                  \
+    if (prof) {                         \
+      const long long now_ = clock64(); \
+      tph[i] += now_ - tlast;           \
+      tlast = now_;                     \
+    }                                   \
+  } while (0)
+  if (prof) tlast = clock64();
+#else
+#define L_STAMP(i) do {} while (0)
+#endif
 
   for (;;) {
     if (tid == 0) { s_next = (int)atomicAdd(g.counter, 1u); s_fail = 0; }
@@ -269,10 +355,11 @@ __global__ void __launch_bounds__(L_THREADS, 4) ck_local_predict_kernel(const __
       const double t0 = g.xyp[2 * c], t1 = g.xyp[2 * c + 1];
       const CkPoint p0 = ck_prepare_point(METRIC, t0, t1);
       const LocalFilter f = local_filter<METRIC>(g, t0, t1);
-      local_scan_segment<METRIC, true>(g, f, p0, 0, warp, lane, off0, pa, pb, pc, pcv, pzv);
-      if (g.n_procs == 2) local_scan_segment<METRIC, true>(g, f, p0, 1, warp, lane, k0 + off1, pa, pb, pc, pcv, pzv);
+      local_scan_segment<METRIC, true, FAST == L_GATHER>(g, f, p0, 0, warp, lane, off0, pa, pb, pc, pcv, pzv);
+      if (g.n_procs == 2) local_scan_segment<METRIC, true, FAST == L_GATHER>(g, f, p0, 1, warp, lane, k0 + off1, pa, pb, pc, pcv, pzv);
     }
     __syncthreads();
+    L_STAMP(0);
 
     // ---- 2. left-looking blocked Cholesky of [Sigma_loc ; c ; z]
     const int kp = (k + LP - 1) / LP * LP, R = kp + 2;
@@ -305,6 +392,13 @@ __global__ void __launch_bounds__(L_THREADS, 4) ck_local_predict_kernel(const __
         // the coordinates while the first operand stage is in flight
         double acc[2][4][2];
         const bool plain = (t > 0) && (i0 + LTM <= k);  // every row is a matrix row below the diagonal block
+        // rows of the identity pad (k <= i < kp) stay e_i through the whole sweep and rows past R do not exist: a warp whose
+        // 16 rows are all of that kind issues no DMMA (it still takes part in the operand staging and the barriers)
+#ifdef CK_LOCAL_NO_SKIP
+        const bool live = true;
+#else
+        const bool live = wrow < R && !(wrow >= k && wrow + 16 <= kp);
+#endif
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
@@ -317,6 +411,7 @@ __global__ void __launch_bounds__(L_THREADS, 4) ck_local_predict_kernel(const __
               else v = (i < R) ? local_entry<METRIC, FAST>(g, i, j, k, kp, k0, pa, pb, pc, pcv, pzv) : 0.0;
               acc[mi][ni][e] = -v;
             }
+        L_STAMP(1);
         if (KT > 0) {
           int rd = 0, wr = LSTG - 1;
           for (int kt = 0; kt < KT; ++kt) {
@@ -326,6 +421,7 @@ __global__ void __launch_bounds__(L_THREADS, 4) ck_local_predict_kernel(const __
             l_cp_commit();
             const double* As = stage + rd * L_STAGE_ELEMS + (16 * warp + g4) * LLD + t4;
             const double* Bs = stage + rd * L_STAGE_ELEMS + (LTM + g4) * LLD + t4;
+            if (live)
 #pragma unroll
             for (int kk = 0; kk < LK; kk += 4) {
               double a[2], b[4];
@@ -351,56 +447,15 @@ __global__ void __launch_bounds__(L_THREADS, 4) ck_local_predict_kernel(const __
           for (int ni = 0; ni < 4; ++ni)
             *reinterpret_cast<double2*>(Wt + (16 * warp + 8 * mi + g4) * LWLD + 8 * ni + 2 * t4) =
                 make_double2(-acc[mi][ni][0], -acc[mi][ni][1]);
+        L_STAMP(2);
         if (t == 0) {
           __syncthreads();
           if (warp == 0) {
-            // ---- D = L_d L_d^T, lane = row; a[kk] holds the UNSCALED column entry until column kk is finished
-            double a[LP];
-#pragma unroll
-            for (int kk = 0; kk < LP; ++kk) a[kk] = Wt[lane * LWLD + kk];
-            int first_bad = 0;
-            double dk = 1.0;
-#pragma unroll
-            for (int kk = 0; kk < LP; ++kk) {
-              const double d = __shfl_sync(0xffffffffu, a[kk], kk);
-              if (!(d > 0.0) && first_bad == 0) first_bad = c0 + kk + 1;
-              if (lane == kk) dk = d;
-              double invd;
-              asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(invd) : "d"(d));
-              invd = fma(fma(-d, invd, 1.0), invd, invd);
-              invd = fma(fma(-d, invd, 1.0), invd, invd);
-              const double u = a[kk];
-              const double w = u * invd;
-#pragma unroll
-              for (int jj = kk + 1; jj < LP; ++jj) {
-                const double ujk = __shfl_sync(0xffffffffu, u, jj);
-                a[jj] = fma(-w, ujk, a[jj]);
-              }
-            }
-            const double sqv = sqrt(dk);
-            const double rsv = 1.0 / sqv;
-            rsd[lane] = rsv;
-            if (lane == 0 && first_bad != 0 && s_fail == 0) s_fail = first_bad;
-#pragma unroll
-            for (int kk = 0; kk < LP; ++kk) {
-              const double rs = __shfl_sync(0xffffffffu, rsv, kk);
-              if (kk <= lane) Wt[lane * LWLD + kk] = (lane == kk) ? sqv : a[kk] * rs;
-            }
-            __syncwarp();
-            // ---- X_d = L_d^-1, lane = column: forward substitution on e_lane, L_d read by broadcast
-            double x[LP];
-#pragma unroll
-            for (int i = 0; i < LP; ++i) x[i] = (i == lane) ? 1.0 : 0.0;
-#pragma unroll
-            for (int kk = 0; kk < LP; ++kk) {
-              x[kk] *= rsd[kk];
-#pragma unroll
-              for (int i = kk + 1; i < LP; ++i) x[i] = fma(-Wt[i * LWLD + kk], x[kk], x[i]);
-            }
-#pragma unroll
-            for (int i = 0; i < LP; ++i) Xd[i * LWLD + lane] = x[i];
+            const int bad = local_diag_block(Wt, Xd, rsd, lane);
+            if (lane == 0 && bad != 0 && s_fail == 0) s_fail = c0 + bad;
           }
           __syncthreads();
+          L_STAMP(3);
         } else {
           __syncwarp();
         }
@@ -438,6 +493,7 @@ __global__ void __launch_bounds__(L_THREADS, 4) ck_local_predict_kernel(const __
             }
           }
         }
+        L_STAMP(4);
       }
     }
     __syncthreads();
@@ -471,7 +527,13 @@ __global__ void __launch_bounds__(L_THREADS, 4) ck_local_predict_kernel(const __
         g.pred[c] = sy; g.sd[c] = sd; g.info[c] = (var > 0.0) ? 0 : -1;  // -1: augmented matrix not PD (warning only)
       }
     }
+    L_STAMP(5);
   }
+#ifdef CK_LOCAL_PROFILE
+  if (prof)
+    for (int i = 0; i < 6; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(g.dbg) + i, (unsigned long long)tph[i]);
+#endif
+#undef L_STAMP
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -512,7 +574,7 @@ struct LocalPlan {
   size_t smem;
 };
 
-static LocalPlan local_plan(ck_i64 m, ck_i64 kmax, int metric) {
+static LocalPlan local_plan(ck_i64 m, ck_i64 kmax, int metric, bool gather = false) {
   LocalPlan p;
   p.kmax = kmax > 0 ? kmax : 1;
   p.kmaxp = (p.kmax + LP - 1) / LP * LP;
@@ -528,8 +590,20 @@ static LocalPlan local_plan(ck_i64 m, ck_i64 kmax, int metric) {
   if (slots > m) slots = m > 0 ? m : 1;
   p.slots = slots;
   const long long narr = (metric == CK_METRIC_HAVERSINE) ? 5 : 4;
-  p.smem = (size_t)(LSTG * L_STAGE_ELEMS + LP * LWLD + LP + L_THREADS + (p.pts_in_ws ? 0 : narr * kcap)) * sizeof(double);
+  const long long recs = gather ? kcap / 2 + 2 * kcap : narr * kcap;
+  p.smem = (size_t)(LSTG * L_STAGE_ELEMS + LP * LWLD + LP + L_THREADS + (p.pts_in_ws ? 0 : recs)) * sizeof(double);
   return p;
+}
+
+// profiling aid (tools): six cycle counters summed over the CTAs of the following ck_local_predict launches
+static long long* g_local_dbg = nullptr;
+extern "C" int ck_local_debug_buffer(void* dev_counters) {
+  g_local_dbg = static_cast<long long*>(dev_counters);
+#ifdef CK_LOCAL_PROFILE
+  return CK_OK;
+#else
+  return dev_counters ? CK_ERR_UNSUPPORTED : CK_OK;  // the product build carries no phase counters
+#endif
 }
 
 extern "C" size_t ck_local_predict_workspace_bytes(ck_i64 m, ck_i64 kmax) {
@@ -568,6 +642,7 @@ static int local_launch(const LocalArgs& g, const LocalPlan& p, cudaStream_t st)
 
 template <int METRIC>
 static int local_dispatch(const LocalArgs& g, const LocalPlan& p, cudaStream_t st) {
+  if (g.sigma) return local_launch<METRIC, L_GATHER>(g, p, st);
   const int mode = g.S[0].mode;
   const bool uniform = mode != CK_NU_GENERIC && g.S[1].mode == mode && g.S[2].mode == mode;
   if (uniform) {
@@ -583,8 +658,9 @@ static int local_dispatch(const LocalArgs& g, const LocalPlan& p, cudaStream_t s
 
 extern "C" int ck_local_predict(const double* xy0, const double* z0, ck_i64 n0, const double* xy1, const double* z1,
                                 ck_i64 n1, const double* xyp, ck_i64 m, const double* params_sigma, const double* params_pred,
-                                int n_procs, int i_pred, int metric, double max_dist, int cv, double c0, const int* k_dev,
-                                const int* seg_dev, ck_i64 kmax, double* pred, double* sd, int* info, void* ws, void* stream) {
+                                int n_procs, int i_pred, int metric, double max_dist, int cv, double c0, const double* sigma,
+                                ck_i64 ld_sigma, const int* k_dev, const int* seg_dev, ck_i64 kmax, double* pred, double* sd,
+                                int* info, void* ws, void* stream) {
   LocalArgs g;
   int rc = local_fill(&g, xy0, z0, n0, xy1, z1, n1, xyp, m, params_sigma, params_pred, n_procs, i_pred, metric, max_dist, cv);
   if (rc) return rc;
@@ -593,9 +669,12 @@ extern "C" int ck_local_predict(const double* xy0, const double* z0, ck_i64 n0, 
   CK_REQUIRE(kmax >= 0, "negative kmax");
   CK_REQUIRE(ws, "workspace is NULL");
   CK_REQUIRE((((uintptr_t)xy0 | (uintptr_t)xy1 | (uintptr_t)ws) & 15) == 0, "coordinate arrays / workspace must be 16-byte aligned");
-  const LocalPlan p = local_plan(m, kmax, metric);
+  const ck_i64 ntot = n0 + ((n_procs == 2) ? n1 : 0);
+  CK_REQUIRE(!sigma || (ld_sigma >= ntot && ntot < (1LL << 31)), "bad leading dimension of the joint covariance");
+  const LocalPlan p = local_plan(m, kmax, metric, sigma != nullptr);
   CK_REQUIRE(p.smem <= 200 * 1024, "kmax too large for the shared-memory plan");
   g.c0 = c0;
+  g.sigma = sigma; g.ld_sigma = ld_sigma;
   g.kcount = k_dev; g.kseg = seg_dev; g.kmax = p.kmax; g.kmaxp = p.kmaxp;
   g.pred = pred; g.sd = sd; g.info = info;
   // the last 256 bytes of the workspace hold the target counter of the persistent CTAs
@@ -604,6 +683,7 @@ extern "C" int ck_local_predict(const double* xy0, const double* z0, ck_i64 n0, 
   g.ws = static_cast<double*>(ws);
   g.slot_stride = p.slot_stride;
   g.pts_in_ws = p.pts_in_ws;
+  g.dbg = g_local_dbg;
   cudaStream_t st = ck_stream(stream);
   CK_CUDA(cudaMemsetAsync(g.counter, 0, sizeof(unsigned int), st));
   if (metric == CK_METRIC_HAVERSINE) return local_dispatch<CK_METRIC_HAVERSINE>(g, p, st);

@@ -49,6 +49,7 @@ class Predictor:
         self.fast_dist = fast_dist
         self._Sigma = None
         self._sigma_params = np.array(mod.params.get_values(), dtype=float)  # Sigma is frozen here (reference :42)
+        self._sigma_dev = None  # the joint covariance on the device (built on first use), gathered by the kernel
         self.cv = False  # placeholder for cross-validation
 
     def _metric(self) -> int:
@@ -60,6 +61,20 @@ class Predictor:
         if self._Sigma is None:
             self._Sigma = self._cov_blocks()
         return self._Sigma
+
+    # largest stacked size for which the N x N joint covariance is kept on the device (8 N^2 bytes: 8.6 GB at the limit);
+    # above it the kernel re-computes the local matrices from the coordinates instead of gathering them
+    sigma_device_max_n = 32768
+
+    def _device_sigma(self, coords_d):
+        """The device counterpart of the reference's stored ``Sigma`` (:98-113): assembled once by K1 from the
+        parameters frozen at construction, then gathered by ck_local_predict for every target."""
+        n = sum(int(c.shape[0]) for c in coords_d)
+        if n == 0 or n > self.sigma_device_max_n:
+            return None
+        if self._sigma_dev is None:
+            self._sigma_dev = ops.joint_cov(coords_d, self._sigma_params, self.n_procs, self._metric())
+        return self._sigma_dev
 
     def _cov_blocks(self) -> dict:
         """Each block of the block-covariance matrix (within a process or between processes)."""
@@ -153,7 +168,8 @@ class Predictor:
         values = [ops.to_device(np.asarray(f.values_main, dtype=float)) for f in self.mf.fields]
         pred, sd, k, info = ops.local_predict(coords, values, ops.coords_to_device(pc), self._sigma_params,
                                               self.n_procs, self.i, self._metric(), max_dist, cv=self.cv,
-                                              params_pred=self.mod.params.get_values(), c0=float(c0))
+                                              params_pred=self.mod.params.get_values(), c0=float(c0),
+                                              sigma=self._device_sigma(coords))
         for row in np.flatnonzero(k == 0):
             warnings.warn(f"No data within maximum distance {max_dist} at location {pc[row]}.")
         for row in np.flatnonzero(info != 0):  # augmented matrix not PD: Schur complement <= 0 or Sigma_loc itself not PD

@@ -47,17 +47,21 @@ def test_c1_point_cokriging_at_size(tag):
     ref_pred, ref_sd, ref_k = g[f"point_pred_{tag}"], g[f"point_sd_{tag}"], g[f"point_k_{tag}"]
     assert ref_k.max() > 380 and ref_k.mean() > 300 and ref_k.min() > 128
     cd = [ops.coords_to_device(grid), ops.coords_to_device(grid)]
-    pred, sd, k, info = ops.local_predict(cd, [ops.to_device(v) for v in z], ops.coords_to_device(pc), pv, 2, 1, METRIC_EUCLID, 0.2)
-    np.testing.assert_array_equal(k, ref_k)  # neighbour sets: bit-exact
     c0 = pv[1] ** 2 + pv[9]
-    e_pred, e_var = relerr(pred, ref_pred), float(np.abs(sd ** 2 - ref_sd ** 2).max() / c0)
-    print(f"\nC1 point {tag}: pred rel {e_pred:.2e}, var/c0 {e_var:.2e}, k {k.min()}..{k.max()}")
     # nugget 0: the local systems have kappa ~ 1e6 and the reference itself is at its rounding floor (~1e-9)
     tol = TOL if tag == "t01" else 2e-8
-    assert (info >= 0).all() or tag == "t0"
-    assert e_pred < tol and e_var < tol
-    big = ref_sd > 1e-3
-    assert relerr(sd[big], ref_sd[big]) < tol
+    # both ways of obtaining the local matrices: re-computed from the coordinates, and gathered from the stored joint
+    # covariance like the reference's np.ix_ (src/point_prediction.py:159-179)
+    for mode, sigma in (("recompute", None), ("gather", ops.joint_cov(cd, pv, 2, METRIC_EUCLID))):
+        pred, sd, k, info = ops.local_predict(cd, [ops.to_device(v) for v in z], ops.coords_to_device(pc), pv, 2, 1,
+                                              METRIC_EUCLID, 0.2, sigma=sigma)
+        np.testing.assert_array_equal(k, ref_k)  # neighbour sets: bit-exact
+        e_pred, e_var = relerr(pred, ref_pred), float(np.abs(sd ** 2 - ref_sd ** 2).max() / c0)
+        print(f"\nC1 point {tag} [{mode}]: pred rel {e_pred:.2e}, var/c0 {e_var:.2e}, k {k.min()}..{k.max()}")
+        assert (info >= 0).all() or tag == "t0"
+        assert e_pred < tol and e_var < tol
+        big = ref_sd > 1e-3
+        assert relerr(sd[big], ref_sd[big]) < tol
     mf = fields.MultiField.from_arrays([grid, grid], z)
     P = point_prediction.Predictor(make_model(pv), mf, fast_dist=False, dist_units=None)
     with warnings.catch_warnings():
