@@ -332,7 +332,12 @@ class BlockCyclicCokriging:
         # (measured on C5, 8 GPUs: 1.83 s without the split, 1.60 s with 40 SMs; CK_MG_PANEL_SMS overrides)
         if isinstance(self.k, CudaKernels):
             self.k.panel_sms = 40 if lookahead else 0
+        # adaptive split (default on): per tile column the SM share of the panel stream is chosen so that the trailing update
+        # of step k and the panel chain of step k + 1, which run side by side, take the same time (CK_MG_PANEL_SMS pins it)
+        self.adaptive_split = lookahead and "CK_MG_PANEL_SMS" not in os.environ
         self.timings = {}
+        self._tracing = bool(int(os.environ.get("CK_MG_TRACE", "0"))) and isinstance(self.k, CudaKernels)
+        self._trace_ev = []
 
     # -- layout ---------------------------------------------------------------------------------
     def _layout(self, N: int, m: int):
@@ -350,6 +355,26 @@ class BlockCyclicCokriging:
         self._layout(N, m)
         tb = self.tb
         return 8 * (self.LRt * tb * self.LCt * tb + 2 * self.g.P * self.LRmax * tb * tb + self.LCt * tb * tb)
+
+    def _panel_share(self, k: int, nsm: int = 148) -> int:
+        """SMs left to the panel stream while trailing update k and panel chain k + 1 run side by side.  Model (fitted to the
+        C3 trace on 2 GPUs, profiles/r02_mg_trace_*): a tile product (tb^3 MACs through the INT8 kernel) costs `tau` SM-ms,
+        the trailing update has ~ rows x cols / 2 of them per rank, the panel chain two per local row tile (column update +
+        TRSM product) plus a fixed latency-bound part (tile Cholesky, its inverse, the broadcasts)."""
+        g = self.g
+        rows = max(self.TR - k - 1, 0)
+        cols = max(self.TC - k - 1, 0)
+        w_main = rows * cols / (2.0 * g.P * g.Q)
+        w_panel = 2.0 * max(self.TR - k - 2, 0) / g.P
+        tau, fixed = 3.65 * (self.tb / 1024.0) ** 3, 1.7
+        best, best_t = 40, float("inf")
+        # never below 40: the NCCL kernels of the look-ahead broadcasts occupy SMs of their own, and a persistent update kernel
+        # whose CTAs cannot all be resident at launch finishes late (static tile partition; measured: profiles/r02_mg_trace_*)
+        for r in range(40, nsm - 23, 4):
+            t = max(w_main * tau / (nsm - r), w_panel * tau / r + fixed)
+            if t < best_t:
+                best, best_t = r, t
+        return best
 
     # -- the sweep --------------------------------------------------------------------------------
     def solve(self, coords: Sequence, z, targets, params, n_procs: int, i_pred: int, metric: int):
@@ -387,12 +412,13 @@ class BlockCyclicCokriging:
         local = K.empty(max(LRt * tb, 1), max(LCt * tb, 1))
         stage = K.empty(2, max(self.LRmax, 1), tb, tb)             # double-buffered: panel tiles of my process row (A operand)
         bcols = K.empty(2, max(LCt, 1), tb, tb)                     # double-buffered: panel tiles of my tile columns (B operand)
-        cmax = (max(LCt, 1) + P - 1) // P + 1
+        cmax = max(LCt, 1)  # one process row may hold ALL of my column tiles (J = q mod Q has a fixed residue mod P when P | Q)
         self._xsend = K.empty(cmax, tb, tb) if P > 1 else None      # column exchange: my contribution / everybody's
         self._xrecv = K.empty(P, cmax, tb, tb) if P > 1 else None
         packs = [K.empty(K.pack_size(tb)) for _ in range(2)]
         info = K.zeros(max(TC, 1), dtype=torch.int32)
         ev = {"t0": self._mark()}
+        self._trace_ev = []
         K.assemble(coords_d, t_d, z_d, params, n_procs, i_pred, metric, tb, g, local)
         ev["t1"] = self._mark()
         with K.stream("main"):
@@ -403,6 +429,8 @@ class BlockCyclicCokriging:
         for k in range(TC):
             buf = k % 2
             nxt = None
+            if self.adaptive_split and isinstance(K, CudaKernels):
+                K.panel_sms = self._panel_share(k)
             if self.lookahead and k + 1 < TC:
                 # column k+1 first (its owners), then its panel, all on the panel stream
                 nxt = self._factor_panel(k + 1, local, stage[1 - buf], bcols[1 - buf], packs[1 - buf], info,
@@ -410,7 +438,9 @@ class BlockCyclicCokriging:
             with K.stream("main"):
                 K.wait(panel_ready)
                 skip = (k + 1) if (self.lookahead and k + 1 < TC) else None
+                self._trace(k, "main_begin")
                 self._trailing_update(k, local, stage[buf], bcols[buf], skip_col=skip)
+                self._trace(k, "main_end")
                 main_done[buf] = K.event()
             if not self.lookahead and k + 1 < TC:
                 nxt = self._factor_panel(k + 1, local, stage[1 - buf], bcols[1 - buf], packs[1 - buf], info, None, main_done[buf])
@@ -499,6 +529,7 @@ class BlockCyclicCokriging:
             if pending is not None:
                 kp, stage_prev, bcols_prev, ready_prev = pending
                 K.wait(ready_prev)
+                self._trace(k, "panel_begin")
                 if q == qk:  # bring column k up to date with panel k-1 (rows I >= k)
                     li0 = first_local_after(k - 1, P, p)
                     if li0 < self.LRt:
@@ -507,18 +538,22 @@ class BlockCyclicCokriging:
                         C = local[li0 * tb: self.LRt * tb, ljk * tb:(ljk + 1) * tb]
                         K.update(A, B, C, tb, li0 * P + p, P, k, Q)
             l0 = first_local_after(k, P, p)
+            self._trace(k, "pending_done")
             if q == qk:
                 if p == pk:
                     lik = k // P
                     K.potrf_tile(local[lik * tb:(lik + 1) * tb, ljk * tb:(ljk + 1) * tb], pack, info[k: k + 1])
                 if P > 1:
                     dist.broadcast(pack, src=g.rank_of(pk, qk), group=g.col_groups[qk])
+                self._trace(k, "potrf_done")
                 if l0 < self.LRt:
                     rows = local[l0 * tb: self.LRt * tb, ljk * tb:(ljk + 1) * tb]
                     K.trsm(pack, tb, rows, stage_b[l0: self.LRt].view(-1, tb))
+                self._trace(k, "trsm_done")
             # A operand: the panel tiles of my process row, from the member of my row that owns tile column k
             if Q > 1 and l0 < self.LRt:
                 dist.broadcast(stage_b[l0: self.LRt], src=g.rank_of(p, qk), group=g.row_groups[p])
+            self._trace(k, "row_bcast_done")
             # B operand: the panel tiles J of my tile columns (J > k); tile J sits with process row J mod P after the row
             # broadcast, so the members of my process column all-gather their shares
             lj0 = first_local_after(k, Q, q)
@@ -541,6 +576,7 @@ class BlockCyclicCokriging:
                     where = {J: pp * cnt + i for pp in range(P) for i, J in enumerate(share[pp])}
                     sel = torch.tensor([where[J] for J in Js], dtype=torch.int64, device=stage_b.device)
                     torch.index_select(recv, 0, sel, out=bcols_b[lj0: self.LCt])
+            self._trace(k, "panel_ready")
             return K.event()
 
     def _trailing_update(self, k: int, local, stage_b, bcols_b, skip_col=None) -> None:
@@ -559,6 +595,19 @@ class BlockCyclicCokriging:
         K.update(A, B, C, tb, li0 * P + p, P, lj0 * Q + q, Q)
 
     # -- timing -----------------------------------------------------------------------------------
+    def _trace(self, k: int, what: str) -> None:
+        """CK_MG_TRACE=1: one CUDA event per (tile column, point of the schedule) on the current stream; `trace_table()`
+        turns them into milliseconds since the start of the sweep (diagnosis of the panel / update overlap)."""
+        if self._tracing:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(torch.cuda.current_stream(self.k.device))
+            self._trace_ev.append((k, what, e))
+
+    def trace_table(self):
+        torch.cuda.synchronize(self.k.device)
+        t0 = self._ev["t1"]
+        return [(k, what, t0.elapsed_time(e)) for k, what, e in self._trace_ev]
+
     def _mark(self):
         if isinstance(self.k, CudaKernels):
             e = torch.cuda.Event(enable_timing=True)

@@ -176,3 +176,33 @@ def test_signature_fixture_is_current(ref):
     mk = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mk)
     assert mk.collect(ref) == json.load(open(os.path.join(GOLDEN, "signatures.json")))
+
+
+def test_bench_reference_arm_line_contract():
+    """bench.py --impl reference prints ONE JSON line with the contract keys, uses every host core even when the
+    launcher exported OMP_NUM_THREADS=1 (torchrun does), and never touches the GPU library."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="2")
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                        "--warmup", "0", "--cpu-n", "300", "--cpu-m", "100", "--cpu-asm-n", "400"], capture_output=True, text=True,
+                       env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["scaling"] == "strong" and d["vs_baseline"] is None
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] == os.cpu_count() and cb["value"] == d["value"] == d["e2e"]["value"]
+    assert cb["value_without_verify"] > cb["value"] and set(cb["scaled_phases_s"]) == {"assemble_s", "verify_s", "factor_s", "solve_s"}
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    env["RANK"] = "1"  # the other ranks exit 0 without work
+    r1 = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2"], capture_output=True,
+                        text=True, env=env, timeout=120)
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
