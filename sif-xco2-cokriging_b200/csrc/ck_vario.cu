@@ -1,11 +1,17 @@
 // ck_vario.cu -- K2: empirical (cross-)semivariogram pair binning for sm_100a.
 //
 // All pairs are visited tile by tile (VA x VB points per CTA, coordinates prepared once in shared
-// memory).  Inside a CTA every lane owns a PRIVATE histogram column in shared memory
-// (layout [warp][bin][lane]: conflict-free, no atomics), so each partial sum is built by exactly one
-// thread in a fixed order; lanes, warps and tiles are then combined by fixed-shape trees.  The
-// decomposition depends only on (na, nb, n_bins) -- never on the device or the launch -- hence the
-// FP64 sums are bit-reproducible and the integer counts are exact.
+// memory).  Histograms live in shared memory:
+//   counts  one u32 array per CTA, updated with the native warp-aggregating shared-memory atomic (ATOMS.POPC.INC):
+//           integer additions are exact and order-free;
+//   sums    FP64, one histogram per WARP with VC = 8 private columns ([warp][bin][column]).  The four lanes that share a
+//           column (lane, lane + 8, lane + 16, lane + 24) update it in four fixed phases, so every column is built by a
+//           fixed sequence of additions -- no atomics, no data-dependent order -- and the eight lanes of a phase hit
+//           eight different banks.  Columns, warps and tiles are then combined by fixed-shape trees.
+// A quarter of the per-lane-column footprint of round 1 (which capped the kernel at 1 CTA = 8 warps per SM, FP64 pipe 21 %
+// active, profiles/r01ab_k2_ncu_full_summary.txt): 50 bins now need 26 KB per CTA, so 5 CTAs (40 warps) share an SM.
+// The decomposition depends only on (na, nb, n_bins) -- never on the device or the launch -- hence the FP64 sums are
+// bit-reproducible and the integer counts are exact.
 // Bin decision = pandas.cut(include_lowest=True) on host-supplied edges: bin k <=> e[k] < d <= e[k+1],
 // d == e[0] -> bin 0, d > e[n_bins] dropped (src/fields.py:208-222).
 #include "ck_common.cuh"
@@ -13,6 +19,7 @@
 constexpr int VA = 128;  // rows of A per tile
 constexpr int VB = 256;  // rows of B per tile
 constexpr int V_MAX_WARPS = 8;
+constexpr int VC = 8;                      // private FP64 sum columns per warp histogram (32 / VC update phases)
 constexpr int V_SMEM_BUDGET = 200 * 1024;  // histogram bytes per CTA
 
 struct VarioGeom {
@@ -30,7 +37,7 @@ static inline bool vario_range(const VarioGeom& g, long long* t0, long long* t1)
   return *t0 >= 0 && *t0 <= *t1 && *t1 <= g.ta;
 }
 static inline int vario_warps(int n_bins) {
-  int w = V_SMEM_BUDGET / (n_bins * 32 * 12);
+  int w = (V_SMEM_BUDGET - n_bins * 4) / (n_bins * VC * 8);
   if (w > V_MAX_WARPS) w = V_MAX_WARPS;
   // power of two so that the warp tree has a fixed shape
   int p = 1;
@@ -261,9 +268,9 @@ template <int METRIC>
 __global__ void __launch_bounds__(256) ck_vario_bin_kernel(VarioBinArgs g, int nwarps, long long ty0) {
   extern __shared__ __align__(16) unsigned char vsm[];
   const int nb_ = g.n_bins;
-  double* hsum = reinterpret_cast<double*>(vsm);                                  // [warp][bin][lane]
-  unsigned int* hcnt = reinterpret_cast<unsigned int*>(hsum + (size_t)nwarps * nb_ * 32);  // [warp][bin][lane]
-  double* edges = reinterpret_cast<double*>(hcnt + (size_t)nwarps * nb_ * 32);   // n_bins + 1
+  double* hsum = reinterpret_cast<double*>(vsm);                                  // [warp][bin][column]
+  double* edges = hsum + (size_t)nwarps * nb_ * VC;                               // n_bins + 1
+  unsigned int* hcnt = reinterpret_cast<unsigned int*>(edges + nb_ + 1);          // [bin], one per CTA
   __shared__ CkPoint pa[VA], pb[VB];
   __shared__ double ra[VA], rb[VB];
   const long long a0 = (ty0 + blockIdx.y) * VA, b0 = (long long)blockIdx.x * VB;
@@ -278,10 +285,8 @@ __global__ void __launch_bounds__(256) ck_vario_bin_kernel(VarioBinArgs g, int n
     }
     return;
   }
-  for (int i = t; i < nwarps * nb_ * 32; i += nthreads) {
-    hsum[i] = 0.0;
-    hcnt[i] = 0u;
-  }
+  for (int i = t; i < nwarps * nb_ * VC; i += nthreads) hsum[i] = 0.0;
+  for (int i = t; i < nb_; i += nthreads) hcnt[i] = 0u;
   for (int i = t; i <= nb_; i += nthreads) edges[i] = g.edges[i];
   for (int i = t; i < VA; i += nthreads)
     if (a0 + i < g.na) {
@@ -294,8 +299,8 @@ __global__ void __launch_bounds__(256) ck_vario_bin_kernel(VarioBinArgs g, int n
       rb[i] = g.vb[b0 + i] - g.mean_b;
     }
   __syncthreads();
-  double* mysum = hsum + (size_t)warp * nb_ * 32 + lane;
-  unsigned int* mycnt = hcnt + (size_t)warp * nb_ * 32 + lane;
+  double* mysum = hsum + (size_t)warp * nb_ * VC + (lane & (VC - 1));
+  const int myphase = lane / VC;
   const double e_last = edges[nb_], e_first = edges[0];
   for (int ia = warp; ia < VA; ia += nwarps) {
     const long long ga = a0 + ia;
@@ -306,13 +311,16 @@ __global__ void __launch_bounds__(256) ck_vario_bin_kernel(VarioBinArgs g, int n
     for (int q = 0; q < VB / 32; ++q) {
       const int ib = lane + 32 * q;
       const long long gb = b0 + ib;
+      int k = -1;  // bin of this lane's pair, -1: nothing to add
+      double v = 0.0;
       if (gb < g.nb && (!g.same_field || gb > ga)) {
         const double d = vario_dist<METRIC>(p, pb[ib]);
         if (d <= g.dlim && d >= e_first) {
-          int k = (int)((d - g.e1) * g.inv_w) + 1;
+          k = (int)((d - g.e1) * g.inv_w) + 1;
           k = k < 0 ? 0 : (k > nb_ - 1 ? nb_ - 1 : k);
           while (k > 0 && d <= edges[k]) --k;
           while (k < nb_ - 1 && d > edges[k + 1]) ++k;
+          bool keep = d <= g.max_dist && d <= e_last;
           if (g.flagged) {
             const double band = g.guard * d;
             const bool near = fabs(d - g.max_dist) <= g.guard * g.max_dist || (k > 0 && d - edges[k] <= band) ||
@@ -320,43 +328,42 @@ __global__ void __launch_bounds__(256) ck_vario_bin_kernel(VarioBinArgs g, int n
             if (near) {
               const unsigned long long pos = atomicAdd(g.flag_count, 1ULL);
               if ((long long)pos < g.flag_capacity) { g.flagged[2 * pos] = ga; g.flagged[2 * pos + 1] = gb; }
-              continue;
+              keep = false;
             }
           }
-          if (!(d <= g.max_dist && d <= e_last)) continue;
-          double v;
-          if (g.covariogram) v = r * rb[ib];
-          else { const double df = r - rb[ib]; v = 0.5 * (df * df); }
-          mysum[k * 32] += v;
-          mycnt[k * 32] += 1u;
+          if (keep) {
+            if (g.covariogram) v = r * rb[ib];
+            else { const double df = r - rb[ib]; v = 0.5 * (df * df); }
+          } else {
+            k = -1;
+          }
         }
       }
+      if (k >= 0) atomicAdd(hcnt + k, 1u);  // ATOMS.POPC.INC: exact, order-free
+      // the 32 / VC lanes that share a sum column take turns, in a fixed order
+#pragma unroll
+      for (int ph = 0; ph < 32 / VC; ++ph)
+        if (myphase == ph && k >= 0) mysum[k * VC] += v;
     }
   }
   __syncthreads();
-  // lanes -> (fixed xor tree), warps -> (fixed tree), one thread writes the tile partial
-  for (int k = warp; k < nb_; k += nwarps) {
+  // columns -> (fixed xor tree over VC lanes), warps -> (fixed tree), one thread writes the tile partial.
+  // A warp handles 32 / VC bins per pass: lane = (bin slot, column).
+  constexpr int BPW = 32 / VC;
+  for (int k0 = warp * BPW; k0 < nb_; k0 += nwarps * BPW) {
+    const int k = k0 + lane / VC, col = lane & (VC - 1);
     double s[V_MAX_WARPS];
-    unsigned int c[V_MAX_WARPS];
     for (int w = 0; w < nwarps; ++w) {
-      double sv = hsum[((size_t)w * nb_ + k) * 32 + lane];
-      unsigned int cv = hcnt[((size_t)w * nb_ + k) * 32 + lane];
+      double sv = (k < nb_) ? hsum[((size_t)w * nb_ + k) * VC + col] : 0.0;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        sv += __shfl_xor_sync(0xffffffffu, sv, o);
-        cv += __shfl_xor_sync(0xffffffffu, cv, o);
-      }
+      for (int o = VC / 2; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
       s[w] = sv;
-      c[w] = cv;
     }
     for (int h = 1; h < nwarps; h <<= 1)
-      for (int w = 0; w + h < nwarps; w += 2 * h) {
-        s[w] += s[w + h];
-        c[w] += c[w + h];
-      }
-    if (lane == 0) {
+      for (int w = 0; w + h < nwarps; w += 2 * h) s[w] += s[w + h];
+    if (col == 0 && k < nb_) {
       g.tile_sums[tile * nb_ + k] = s[0];
-      g.tile_counts[tile * nb_ + k] = c[0];
+      g.tile_counts[tile * nb_ + k] = hcnt[k];
     }
   }
 }
@@ -457,7 +464,7 @@ extern "C" int ck_vario_bin_tiles(const double* xya, const double* va, ck_i64 na
   const bool guard = flagged && metric == CK_METRIC_HAVERSINE;  // Euclidean distances are exact: no guard
   g.flagged = guard ? flagged : nullptr; g.flag_capacity = flag_capacity; g.flag_count = flag_count;
   g.guard = CK_VARIO_GUARD; g.dlim = guard ? vario_dlim(metric, max_dist) : max_dist;
-  const size_t smem = (size_t)nwarps * n_bins * 32 * 12 + (size_t)(n_bins + 1) * 8 + 16;
+  const size_t smem = (size_t)nwarps * n_bins * VC * 8 + (size_t)(n_bins + 1) * 8 + (size_t)n_bins * 4 + 16;
   dim3 grid((unsigned)geo.tb, (unsigned)(t1 - t0));
   if (metric == CK_METRIC_HAVERSINE) {
     CK_CUDA(cudaFuncSetAttribute(ck_vario_bin_kernel<CK_METRIC_HAVERSINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
