@@ -1,7 +1,8 @@
 // ck_matern.cu -- K1: fused distance + Matern (cross-)covariance assembly for sm_100a.
 //
 // One CTA produces one 64 x 64 tile of a block: the two coordinate tiles are staged once in shared
-// memory (prepared per point: radians and cos(lat) for haversine), each thread evaluates 16 entries
+// memory (prepared per point; for haversine covariance blocks: the half-angle sines / cosines and cos(lat), so that a
+// pair needs no sine evaluation at all -- ck_dist_haversine_pre), each thread evaluates 16 entries
 // in registers (independent chains -> ILP on the FP64 pipe), and rows are written with 256-byte
 // coalesced warp stores.  The optional mirrored copy (symmetric blocks, C01 -> C10) goes through a
 // padded shared-memory transpose so that it is written coalesced as well: the matrix is written
@@ -59,6 +60,23 @@ int ck_block_matern(const CkParams& p, int i, int j, int use_nugget, CkMatern* o
 constexpr int TILE = 64;
 constexpr int K1_THREADS = 256;
 
+// per-point record and pair distance of one kernel variant: covariance blocks on the sphere use the precomputed
+// half-angle form, everything else (Euclid; distance output in the reference's operation order) the plain point
+template <int METRIC, int VALUE>
+struct K1Point {
+  using type = CkPoint;
+  static __device__ __forceinline__ type prepare(double a, double b) { return ck_prepare_point(METRIC, a, b); }
+  static __device__ __forceinline__ double dist(const type& p, const type& q) {
+    return VALUE ? ck_dist_fast<METRIC>(p, q) : ck_dist<METRIC>(p, q);
+  }
+};
+template <>
+struct K1Point<CK_METRIC_HAVERSINE, 1> {
+  using type = CkPointH;
+  static __device__ __forceinline__ type prepare(double a, double b) { return ck_prepare_point_h(a, b); }
+  static __device__ __forceinline__ double dist(const type& p, const type& q) { return ck_dist_haversine_pre(p, q); }
+};
+
 // VALUE: 0 = distance only, 1 = covariance
 template <int METRIC, int MODE, int VALUE>
 __global__ void __launch_bounds__(K1_THREADS, (MODE == CK_NU_GENERIC && VALUE) ? 2 : 4) ck_block_kernel(const double* __restrict__ xy1, long long n1,
@@ -68,16 +86,17 @@ __global__ void __launch_bounds__(K1_THREADS, (MODE == CK_NU_GENERIC && VALUE) ?
                                                               int symmetric) {
   const long long bi = blockIdx.y, bj = blockIdx.x;
   if (symmetric && bj < bi) return;  // mirrored from the upper tile
-  __shared__ CkPoint pr[TILE], pc[TILE];
+  using PT = K1Point<METRIC, VALUE>;
+  __shared__ typename PT::type pr[TILE], pc[TILE];
   __shared__ double tr[TILE][TILE + 1];
   const int t = threadIdx.x;
   const long long r0 = bi * TILE, c0 = bj * TILE;
   if (t < TILE) {
     const long long r = r0 + t;
-    if (r < n1) pr[t] = ck_prepare_point(METRIC, xy1[2 * r], xy1[2 * r + 1]);
+    if (r < n1) pr[t] = PT::prepare(xy1[2 * r], xy1[2 * r + 1]);
   } else if (t < 2 * TILE) {
     const long long c = c0 + (t - TILE);
-    if (c < n2) pc[t - TILE] = ck_prepare_point(METRIC, xy2[2 * c], xy2[2 * c + 1]);
+    if (c < n2) pc[t - TILE] = PT::prepare(xy2[2 * c], xy2[2 * c + 1]);
   }
   __syncthreads();
   const int tx = t & 31, ty = t >> 5;  // 8 warps; warp `ty` owns rows ty, ty+8, ...
@@ -91,13 +110,10 @@ __global__ void __launch_bounds__(K1_THREADS, (MODE == CK_NU_GENERIC && VALUE) ?
       const int lc = tx + 32 * c;
       double val = 0.0;
       if (r0 + lr < n1 && c0 + lc < n2) {
-        if (VALUE && MODE != CK_NU_GENERIC) {  // assembly, closed-form orders: branch-free fast math (ck_math.cuh)
-          val = ck_matern_cov_fast<MODE>(P, ck_dist_fast<METRIC>(pr[lr], pc[lc]));
-        } else if (VALUE) {  // assembly, generic order: fast distance, K_nu by series / continued fraction
-          val = ck_matern_cov<MODE>(P, ck_dist_fast<METRIC>(pr[lr], pc[lc]));
-        } else {             // distance output: reference operation order (bit-identical Euclidean distances)
-          val = ck_dist<METRIC>(pr[lr], pc[lc]);
-        }
+        const double h = PT::dist(pr[lr], pc[lc]);
+        if (VALUE && MODE != CK_NU_GENERIC) val = ck_matern_cov_fast<MODE>(P, h);  // closed-form orders: branch-free fast math
+        else if (VALUE) val = ck_matern_cov<MODE>(P, h);                          // generic order: K_nu by series / Chebyshev fits
+        else val = h;                                                             // distance output: reference operation order
       }
       v[r][c] = val;
     }

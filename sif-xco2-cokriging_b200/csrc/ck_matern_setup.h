@@ -96,10 +96,10 @@ static inline int ck_matern_setup(CkMatern* P, double scale, double nu, double l
   P->nl = nl;
   P->mu = (double)mu;
   P->mu2 = (double)m2;
-  P->gam1 = (double)(-odd);             // (1/G(1-mu) - 1/G(1+mu)) / (2 mu)
-  P->gam2 = (double)even;               // (1/G(1-mu) + 1/G(1+mu)) / 2
-  P->gampl = (double)(even + mu * odd); // 1/Gamma(1+mu)
-  P->gammi = (double)(even - mu * odd); // 1/Gamma(1-mu)
+  P->temme_g1 = (double)(-odd);             // (1/G(1-mu) - 1/G(1+mu)) / (2 mu)
+  P->temme_g2 = (double)even;               // (1/G(1-mu) + 1/G(1+mu)) / 2
+  P->rgam_plus = (double)(even + mu * odd); // 1/Gamma(1+mu)
+  P->rgam_minus = (double)(even - mu * odd); // 1/Gamma(1-mu)
   for (int i = 0; i < CK_KNU_TT; ++i) {
     const long double fi = (long double)i;
     P->t_rq[i] = i ? (double)(1.0L / (fi * fi - m2)) : 0.0;
@@ -156,6 +156,6 @@ static inline int ck_matern_setup(CkMatern* P, double scale, double nu, double l
     P->cheb_ok = 1;
   }
   const long double pm = 3.14159265358979323846264338327950288L * mu;
-  P->pimu = (fabsl(pm) < 1.0e-9L) ? 1.0 : (double)(pm / sinl(pm));
+  P->mu_pi_ratio = (fabsl(pm) < 1.0e-9L) ? 1.0 : (double)(pm / sinl(pm));
   return 0;
 }

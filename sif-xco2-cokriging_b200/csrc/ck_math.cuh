@@ -106,9 +106,9 @@ struct CkMatern {
   double lc;         // (1 - nu) ln 2 - lgamma(nu)
   // generic-nu constants (Temme): nu = nl + mu, |mu| <= 1/2
   double mu, mu2;
-  double gam1, gam2;    // (1/G(1-mu) -/+ 1/G(1+mu)) / (2mu | 2)
-  double gampl, gammi;  // 1/Gamma(1+mu), 1/Gamma(1-mu)
-  double pimu;          // pi mu / sin(pi mu)
+  double temme_g1, temme_g2;    // (1/G(1-mu) -/+ 1/G(1+mu)) / (2mu | 2)
+  double rgam_plus, rgam_minus;  // 1/Gamma(1+mu), 1/Gamma(1-mu)
+  double mu_pi_ratio;          // pi mu / sin(pi mu)
   int nl;
   int mode;  // CK_NU_*
   // reciprocal tables of the K_nu iterations (depend on mu and the iteration index only; filled by ck_matern_setup):
@@ -142,21 +142,26 @@ __device__ __forceinline__ double ck_rcp(double x) {
 #define CK_KNU_EPS 1.0e-16
 #define CK_KNU_MAXIT 400
 
-// Modified Bessel function of the second kind K_nu(x), x > 0, nu = P.nl + P.mu.
+// Modified Bessel function of the second kind K_nu(x), x > 0, nu = P.nl + P.mu, |mu| <= 1/2:
+//   K_mu, K_mu+1 (k_lo, k_hi) from N. M. Temme's series (J. Comput. Phys. 19 (1975) 324, eqs. 1.3-1.9) for x <= 2,
+//   from per-block Chebyshev fits of sqrt(x) e^x K(x) in 2 / x (x > 2; fallback: Steed's continued fraction CF2),
+//   then the forward recurrence K_(o+1) = (2 o / x) K_o + K_(o-1), which is stable for K.
+// All constants that depend on mu alone (Temme's Gamma_1, Gamma_2, the reciprocal Gamma values, the reciprocals of the
+// series / continued-fraction indices, the Chebyshev coefficients) come from ck_matern_setup (host, long double).
 CK_HD double ck_besselk(const CkMatern& P, double x) {
   const double mu = P.mu, mu2 = P.mu2;
   const double xi = 1.0 / x, xi2 = 2.0 * xi;
-  double rkmu, rk1;
-  if (x <= 2.0) {  // Temme's series for K_mu, K_mu+1
+  double k_lo, k_hi;
+  if (x <= 2.0) {  // Temme's series: K_mu = sum c_k f_k, K_mu+1 = (2 / x) sum c_k (p_k - k f_k), c_k = (x^2 / 4)^k / k!
     const double b = 0.5 * x;
     double d = -log(b);
     double e = mu * d;
     const double fact2 = (fabs(e) < 1.0e-6) ? 1.0 + e * e * (1.0 / 6.0) : sinh(e) / e;
-    double ff = P.pimu * (P.gam1 * cosh(e) + P.gam2 * fact2 * d);
+    double ff = P.mu_pi_ratio * (P.temme_g1 * cosh(e) + P.temme_g2 * fact2 * d);
     double sum = ff;
     e = exp(e);
-    double p = 0.5 * e / P.gampl;
-    double q = 0.5 / (e * P.gammi);
+    double p = 0.5 * e / P.rgam_plus;
+    double q = 0.5 / (e * P.rgam_minus);
     double c = 1.0;
     d = b * b;
     double sum1 = p;
@@ -178,8 +183,8 @@ CK_HD double ck_besselk(const CkMatern& P, double x) {
       sum1 += c * (p - fi * ff);
       if (fabs(del) < fabs(sum) * CK_KNU_EPS) break;
     }
-    rkmu = sum;
-    rk1 = sum1 * xi2;
+    k_lo = sum;
+    k_hi = sum1 * xi2;
   } else if (P.cheb_ok) {  // Chebyshev expansions of sqrt(x) e^x K(x) in t = 2 / x (Clenshaw, both orders at once)
     const double t = 2.0 * xi;
     const int seg = t <= 0.25 ? 0 : (t <= 0.5 ? 1 : 2);
@@ -196,8 +201,8 @@ CK_HD double ck_besselk(const CkMatern& P, double x) {
     const double g0 = fma(u, b1, P.cheb[0][seg][0] - b2);
     const double g1 = fma(u, d1, P.cheb[1][seg][0] - d2);
     const double w = exp(-x) * sqrt(xi);  // e^-x / sqrt(x)
-    rkmu = g0 * w;
-    rk1 = g1 * w;
+    k_lo = g0 * w;
+    k_hi = g1 * w;
   } else {  // Steed's algorithm, continued fraction CF2
     double b = 2.0 * (1.0 + x);
     double d = 1.0 / b;
@@ -229,15 +234,15 @@ CK_HD double ck_besselk(const CkMatern& P, double x) {
       if (fabs(dels) < fabs(s) * CK_KNU_EPS) break;
     }
     h = a1 * h;
-    rkmu = sqrt(1.5707963267948966 * xi) * exp(-x) / s;
-    rk1 = rkmu * (mu + x + 0.5 - h) * xi;
+    k_lo = sqrt(1.5707963267948966 * xi) * exp(-x) / s;
+    k_hi = k_lo * (mu + x + 0.5 - h) * xi;
   }
   for (int i = 1; i <= P.nl; ++i) {
-    const double t = (mu + (double)i) * xi2 * rk1 + rkmu;
-    rkmu = rk1;
-    rk1 = t;
+    const double t = (mu + (double)i) * xi2 * k_hi + k_lo;
+    k_lo = k_hi;
+    k_hi = t;
   }
-  return rkmu;
+  return k_lo;
 }
 
 // K_nu(x) < AMOS cut-off for the closed-form orders (mode = CK_NU_HALF .. CK_NU_7HALF): scipy's kv returns exactly 0 there
@@ -420,6 +425,38 @@ CK_HD double ck_dist_haversine_fast(const CkPoint& p, const CkPoint& q) {
 template <int METRIC>
 CK_HD double ck_dist_fast(const CkPoint& p, const CkPoint& q) {
   return METRIC == CK_METRIC_HAVERSINE ? ck_dist_haversine_fast(p, q) : ck_dist_euclid_fast(p, q);
+}
+
+// Haversine with PER-POINT half-angle trigonometry: sin((x1 - x2) / 2) = sin(x1/2) cos(x2/2) - cos(x1/2) sin(x2/2),
+// so a pair costs two products and a difference per angle instead of a range reduction + a degree-15 sine polynomial:
+// ~70 -> ~45 FP64 instructions per distance.  The two products are rounded separately (no FMA contraction), hence the
+// difference is EXACTLY 0 for identical points (the h == 0 nugget decision) -- also across the antimeridian, since
+// sin^2 of the half difference is pi-periodic.  Cancellation leaves an ABSOLUTE error of ~4e-16 in each half-angle sine,
+// i.e. <= ~7e-12 km in the distance (2e-12 relative at 3 km, 1e-15 at 5000 km): inside the 1e-12 relative tolerance of
+// the covariance entries (rho'(h) h / rho -> 0 as h -> 0), but outside the guard band of the variogram bin decisions --
+// so only the ASSEMBLY kernel (K1) uses it; K2 / K4 keep the direct forms.
+struct CkPointH {
+  double sa, ca;  // sin(lat / 2), cos(lat / 2)
+  double sb, cb;  // sin(lon / 2), cos(lon / 2)
+  double c;       // cos(lat)
+};
+
+CK_HD CkPointH ck_prepare_point_h(double lat_deg, double lon_deg) {
+  CkPointH q;
+  const double a = CK_MUL(lat_deg, CK_DEG2RAD), b = CK_MUL(lon_deg, CK_DEG2RAD);
+  q.sa = sin(0.5 * a);
+  q.ca = cos(0.5 * a);
+  q.sb = sin(0.5 * b);
+  q.cb = cos(0.5 * b);
+  q.c = cos(a);
+  return q;
+}
+
+CK_HD double ck_dist_haversine_pre(const CkPointH& p, const CkPointH& q) {
+  const double s0 = CK_SUB(CK_MUL(p.sa, q.ca), CK_MUL(p.ca, q.sa));
+  const double s1 = CK_SUB(CK_MUL(p.sb, q.cb), CK_MUL(p.cb, q.sb));
+  const double a = CK_FMA(p.c * q.c, s1 * s1, s0 * s0);
+  return ck_fast_asin_sqrt(a) * (2.0 * CK_EARTH_RADIUS);
 }
 
 // sigma^2 rho(h) (+ nugget where h == 0) for the closed-form orders nu in {1/2, 3/2, 5/2, 7/2}, branch-free:

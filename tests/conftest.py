@@ -94,6 +94,14 @@ def hostmath():
         lib.ckh_fast_pieces(x.ctypes.data_as(dp), ctypes.c_long(x.size), *(v.ctypes.data_as(dp) for v in o))
         return o
 
+    def _dist_pre(X1, X2):
+        X1, X2 = np.ascontiguousarray(X1, float), np.ascontiguousarray(X2, float)
+        out = np.empty((len(X1), len(X2)))
+        lib.ckh_distance_pre(X1.ctypes.data_as(dp), ctypes.c_long(len(X1)), X2.ctypes.data_as(dp), ctypes.c_long(len(X2)),
+                             out.ctypes.data_as(dp))
+        return out
+
+    H.distance_pre = staticmethod(_dist_pre)
     H.distance_fast = staticmethod(_dist_fast)
     H.matern_cov_fast = staticmethod(_matern_fast)
     H.fast_pieces = staticmethod(_pieces)

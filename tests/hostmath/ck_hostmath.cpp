@@ -45,6 +45,14 @@ int ckh_distance_fast(int metric, const double* X1, long n1, const double* X2, l
   return 0;
 }
 
+int ckh_distance_pre(const double* X1, long n1, const double* X2, long n2, double* out) {
+  for (long i = 0; i < n1; ++i) {
+    const CkPointH p = ck_prepare_point_h(X1[2 * i], X1[2 * i + 1]);
+    for (long j = 0; j < n2; ++j) out[i * n2 + j] = ck_dist_haversine_pre(p, ck_prepare_point_h(X2[2 * j], X2[2 * j + 1]));
+  }
+  return 0;
+}
+
 int ckh_matern_cov_fast(double scale, double nu, double len_scale, double nugget, const double* h, long n, double* out) {
   CkMatern P;
   if (ck_matern_setup(&P, scale, nu, len_scale, nugget)) return -1;

@@ -110,6 +110,34 @@ def test_fast_distances_vs_reference_fixture(hostmath):
     assert np.abs(a - b).max() < 1e-8  # km
 
 
+def test_precomputed_half_angle_haversine(hostmath):
+    """K1's pair distance on the sphere (ck_dist_haversine_pre: per-point half-angle sines / cosines, no sine per pair):
+    exact zeros for identical points, <= 1e-11 km absolute from the reference-order function (the cancellation bound),
+    and covariance entries inside the 1e-12 relative tolerance on the 0.05 degree lattice (min distance 3 km)."""
+    g = golden("distances")
+    d = hostmath.distance_pre(g["X1"], g["X2"])
+    assert ((d == 0) == (g["hav"] == 0)).all()
+    assert np.abs(d - g["hav"]).max() < 1e-11
+    nz = g["hav"] > 0
+    assert relerr(d[nz], g["hav"][nz]) < 2e-12
+    rng = np.random.default_rng(5)
+    X = np.c_[rng.uniform(-90, 90, 300), rng.uniform(-180, 180, 300)]
+    X[:4] = [[90, 0], [-90, 10], [0, 180], [0, -180]]
+    a, b = hostmath.distance_pre(X, X), hostmath.distance(1, X, X)
+    assert (np.diagonal(a) == 0).all() and a[2, 3] < 1e-9  # (0, 180) and (0, -180) are the same point
+    off = (b > 1e-6) & (b < 19000.0)
+    assert (np.abs(a - b)[off] < 1e-11 + 4e-15 * b[off]).all()  # absolute (cancellation) + relative (asin amplification) parts
+    # covariance entries on a dense lattice: every closed-form order within 1e-12 relative of the reference formula
+    lat, lon = np.arange(30.025, 31.5, 0.05), np.arange(-100.975, -99.5, 0.05)
+    L = np.array([(u, v) for u in lat for v in lon])
+    ref_h = orc.distance_matrix(L, L, fast_dist=True)
+    got_h = hostmath.distance_pre(L, L)
+    for nu, ell in ((0.5, 100.0), (1.5, 500.0), (2.5, 300.0), (3.5, 100.0)):
+        ref = orc.matern_correlation(nu, ell, ref_h)
+        got = hostmath.matern_cov_fast(1.0, nu, ell, 0.0, got_h.ravel()).reshape(ref.shape)
+        assert relerr(got, ref) < 1e-12, (nu, ell)
+
+
 def test_fast_matern_vs_reference_fixture(hostmath):
     g = golden("matern")
     for a, nu in enumerate(g["nus"]):
