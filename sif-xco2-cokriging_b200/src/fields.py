@@ -7,7 +7,10 @@ Public names and signatures follow /root/reference/src/fields.py:20-403.  The ho
 pair plus pandas categoricals, fields.py:192-222).  xarray-based preprocessing (``Field`` for real
 data, ``_preprocess_ds``, ``fit_ols``) is host-only O(n) work outside the hot path and is kept
 behind a lazy ``import xarray``; ``Field.from_arrays`` / ``MultiField.from_arrays`` build the same
-objects straight from numpy arrays.
+objects straight from numpy arrays, and ``preprocess_arrays`` / ``Field.from_cube`` /
+``MultiField.from_cubes`` run the reference's whole preprocessing chain (temporal linear trend of the
+spatial mean, OLS spatial trend on standardised covariates, standardisation; fields.py:283-375) on a
+plain ``(time, lat, lon)`` numpy cube -- no xarray at run time.
 
 Preserved semantics: rows are [lat, lon] degrees (haversine x 6371 km) or
 [x, y] (Euclidean, ``units=None``); residuals use the mean of ALL values; marginal variograms use
@@ -102,9 +105,45 @@ class Field:
         self.ds = self.ds_main = None
         return self
 
+    @classmethod
+    def from_cube(cls, cube, lat, lon, t_index: int, covariates=None, timestamp=np.nan, main_mask=None,
+                  variance=None, data_name: str = "value") -> "Field":
+        """The reference's ``Field(ds, covariates, timestamp, type="real")`` (fields.py:64-95) from plain arrays:
+        ``cube`` is (time, lat, lon) with NaN for missing cells, ``t_index`` selects the time slice, ``covariates`` as in
+        ``preprocess_arrays``; ``main_mask`` (lat, lon) marks the base-grid cells (``get_main_coords``); rows are ordered
+        (lon, lat) like the data frame of a (lon, lat, time) dataset."""
+        pre = preprocess_arrays(cube, lat, lon, t_index, covariates)
+        self = object.__new__(cls)
+        self.timestamp = timestamp
+        self.data_name, self.var_name = data_name, data_name + "_var"
+        self.ds = self.ds_main = None
+        self.attrs = pre["attrs"]
+        df = pre["frame"]
+        keep = df["value"].notna().values
+        self.coords = df.loc[keep, ["lat", "lon"]].values
+        self.values = df.loc[keep, "value"].values
+        if main_mask is None:
+            self.coords_main, self.values_main = self.coords, self.values
+        else:
+            mm = np.asarray(main_mask, dtype=bool).T.ravel()[keep]  # frame rows are (lon, lat) ordered
+            self.coords_main, self.values_main = self.coords[mm], self.values[mm]
+        self.temporal_trend = self.attrs["temporal_trend"]
+        self.spatial_trend = df.loc[keep, "spatial_trend"].values
+        self.spatial_mean = self.attrs["spatial_mean"]
+        self.scale_fact = self.attrs["scale_fact"]
+        self.covariate_means = self.attrs["covariate_means"]
+        self.covariate_scales = self.attrs["covariate_scales"]
+        self.variance_estimate = None if variance is None else np.asarray(variance, dtype=float)[t_index].T.ravel()[keep]
+        self.covariates = df.loc[keep, pre["covariate_names"]]
+        self.size = len(self.values)
+        return self
+
     def to_dataframe(self, main: bool = False):
         """Converts the field to a data frame."""
         ds = self.ds_main if main else self.ds
+        if ds is None:  # array-built field
+            c, v = (self.coords_main, self.values_main) if main else (self.coords, self.values)
+            return pd.DataFrame({"lat": c[:, 0], "lon": c[:, 1], self.data_name: v})
         return ds.to_dataframe().reset_index().dropna(subset=[self.data_name])
 
     def to_xarray(self):
@@ -154,6 +193,27 @@ class MultiField:
         for k, f in enumerate(fields):
             self.fields[k] = f
         self.n_procs = len(self.fields)
+        self.n_data = self._count_data()
+        return self
+
+    @classmethod
+    def from_cubes(cls, cubes: list, lats: list, lons: list, t_indices: list, covariates: list = None, timestamp=np.nan,
+                   timedeltas=None, main_masks: list = None) -> "MultiField":
+        """``MultiField(datasets, covariates, timestamp, timedeltas)`` for real data (fields.py:135-171) from plain
+        (time, lat, lon) cubes: one ``Field.from_cube`` per process."""
+        n = len(cubes)
+        self = object.__new__(cls)
+        self.type = "real"
+        self.datasets = None
+        self.timestamp = timestamp
+        self.timedeltas = [np.nan] * n if timedeltas is None else timedeltas
+        self.covariates = covariates
+        cov = [None] * n if covariates is None else covariates
+        mm = [None] * n if main_masks is None else main_masks
+        self.fields = np.empty(n, dtype=object)
+        for k in range(n):
+            self.fields[k] = Field.from_cube(cubes[k], lats[k], lons[k], t_indices[k], cov[k], timestamp, mm[k])
+        self.n_procs = n
         self.n_data = self._count_data()
         return self
 
@@ -334,6 +394,72 @@ def fit_ols(ds, data_name: str, covar_names: list):
     out["ols_mean"] = model.predict(covariates)
     ds_pred = out.set_index(["lon", "lat"]).to_xarray().assign_coords(coords={"time": ds[data_name].time})
     return ds_pred["ols_mean"], model, means, scales
+
+
+# ------------------------------------------------------------------------------------------------
+# The preprocessing chain on plain arrays (no xarray): same steps, same library calls as fields.py:283-375
+def fit_linear_trend_array(cube: np.ndarray) -> np.ndarray:
+    """``fit_linear_trend`` (fields.py:283-287): linear trend over time of the spatial mean of every time slice
+    (NaN cells skipped, as xarray's ``mean`` does); returns the trend value per time step."""
+    from stat_tools import simple_linear_regression
+    cube = np.asarray(cube, dtype=float)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", category=RuntimeWarning)  # all-NaN slices -> NaN, like xarray
+        x = np.nanmean(cube.reshape(cube.shape[0], -1), axis=1)
+    return simple_linear_regression(x)
+
+
+def fit_ols_frame(df: pd.DataFrame, data_name: str, covar_names: list):
+    """``fit_ols`` (fields.py:290-315) on a data frame with columns lon, lat, `data_name` and the covariates: OLS of
+    the data on the STANDARDISED covariates (sample std, ddof = 1, like pandas).  Returns (frame [lon, lat, ols_mean]
+    of the rows with data, fitted sklearn model, covariate means, covariate scales)."""
+    from sklearn.linear_model import LinearRegression
+    d = df.dropna(subset=[data_name]).reset_index(drop=True)
+    if d.shape[0] == 0:
+        return d[["lon", "lat"]].assign(ols_mean=np.nan), None, None, None
+    means = d[covar_names].mean(axis=0, skipna=True).values
+    scales = d[covar_names].std(axis=0, skipna=True).values
+    covariates = d[covar_names].copy()
+    for i, name in enumerate(covar_names):
+        covariates[name] = (covariates[name] - means[i]) / scales[i]
+    model = LinearRegression().fit(covariates, d[data_name])
+    out = d[["lon", "lat"]].copy()
+    out["ols_mean"] = model.predict(covariates)
+    return out, model, means, scales
+
+
+def preprocess_arrays(cube, lat, lon, t_index: int, covariates=None) -> dict:
+    """``_preprocess_ds`` (fields.py:345-375) on a (time, lat, lon) cube: (1) subtract the linear temporal trend of the
+    spatial means, (2) take slice `t_index`, (3) subtract the OLS spatial trend fitted on standardised covariates,
+    (4) standardise the residuals (nanmean / nanstd).  ``covariates``: None or a list of names among "lon", "lat"
+    (default ["lon", "lat"], what the reference uses when no covariate dataset is given), or a dict name -> (lat, lon)
+    array.  Returns {"frame": rows ordered (lon, lat) with columns lon, lat, value (standardised residual, NaN where
+    missing), spatial_trend and the covariates; "attrs": temporal_trend, spatial_model, covariate_means,
+    covariate_scales, spatial_mean, scale_fact; "covariate_names"}."""
+    cube = np.asarray(cube, dtype=float)
+    lat, lon = np.asarray(lat, dtype=float), np.asarray(lon, dtype=float)
+    trend = fit_linear_trend_array(cube)
+    field = cube[t_index] - trend[t_index]                      # (lat, lon)
+    LON, LAT = np.meshgrid(lon, lat, indexing="ij")              # (lon, lat): row order of a (lon, lat, time) dataset
+    df = pd.DataFrame({"lon": LON.ravel(), "lat": LAT.ravel(), "value": field.T.ravel()})
+    if covariates is None:
+        names = ["lon", "lat"]
+    elif isinstance(covariates, dict):
+        names = list(covariates)
+        for name in names:
+            df[name] = np.asarray(covariates[name], dtype=float).T.ravel()
+    else:
+        names = list(covariates)
+    ols, model, means, scales = fit_ols_frame(df, "value", names)
+    df = df.merge(ols.rename(columns={"ols_mean": "spatial_trend"}), on=["lon", "lat"], how="left")
+    resid = df["value"].values - df["spatial_trend"].values
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", category=RuntimeWarning)
+        mean, scale = np.nanmean(resid), np.nanstd(resid)
+    df["value"] = (resid - mean) / scale
+    attrs = {"temporal_trend": trend[t_index], "spatial_model": model, "covariate_means": means, "covariate_scales": scales,
+             "spatial_mean": mean, "scale_fact": scale}
+    return {"frame": df, "attrs": attrs, "covariate_names": names}
 
 
 def distance_matrix(X1: np.ndarray, X2: np.ndarray, units: str = "km", fast_dist: bool = False) -> np.ndarray:

@@ -153,7 +153,28 @@ class Predictor:
         coords_d, _ = self._device_data(cv_ix)
         return ops.joint_cov(coords_d, self.mod.params.get_values(), self.n_procs, self._metric()).cpu().numpy()
 
-    # -- back-transform (host, xarray) -------------------------------------------------------------
+    # -- back-transform ------------------------------------------------------------------------------
+    def postprocess_frame(self, df: pd.DataFrame) -> pd.DataFrame:
+        """``_postprocess_predictions`` (:155-205) without xarray: `df` has columns lat, lon, pred, pred_err on the
+        standardised scale; returns the same columns on the original data scale -- pred * scale_fact + spatial_mean +
+        OLS trend(standardised covariates) + temporal trend, pred_err * scale_fact.  ``self.covariates``: None (lon / lat
+        are the covariates) or a data frame with columns lon, lat and one column per covariate of the fit."""
+        field = self.mf.fields[self.i]
+        attrs = field.attrs if getattr(field, "ds", None) is None else field.ds.attrs
+        out = df[["lat", "lon", "pred", "pred_err"]].copy()
+        out["pred"] = out["pred"] * attrs["scale_fact"] + attrs["spatial_mean"]
+        out["pred_err"] = out["pred_err"] * attrs["scale_fact"]
+        if self.covariates is None:
+            covariates = out[["lon", "lat"]].copy()
+        else:
+            names = [c for c in self.covariates.columns if c not in ("lon", "lat")]
+            out = out.merge(self.covariates, on=["lon", "lat"], how="left").dropna(subset=names).reset_index(drop=True)
+            covariates = out[names].copy()
+        for k, name in enumerate(covariates):
+            covariates[name] = (covariates[name] - attrs["covariate_means"][k]) / attrs["covariate_scales"][k]
+        out["pred"] = out["pred"] + attrs["spatial_model"].predict(covariates) + attrs["temporal_trend"]
+        return out[["lat", "lon", "pred", "pred_err"]]
+
     def _postprocess_predictions(self, df: pd.DataFrame):
         """Convert prediction results to a dataset on the original data scale: undo the
         standardisation, add the OLS spatial trend and the temporal trend (host-only, xarray)."""

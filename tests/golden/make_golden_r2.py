@@ -11,6 +11,11 @@
                    standard-normal values, VarioConfig(max_dist=1500, n_bins=50): MultiField.get_variogram for
                    (0, 0), (0, 1), (1, 1) -- 5e7 / 1e8 / 5e7 pairs through the reference's pandas path.
   variogram_cloud.npz   MultiField._variogram_cloud on a small case (both kinds).
+  preprocess.npz   the preprocessing / back-transform chain (src/fields.py:283-375, src/joint_prediction.py:155-205) on a
+                   tiny (time, lat, lon) cube.  xarray is not installed here, so the Dataset plumbing of those functions
+                   cannot run; the fixture executes their NUMERIC steps in order with the reference's own callee
+                   (stat_tools.simple_linear_regression, unmodified) and the same library calls (sklearn LinearRegression
+                   on pandas-standardised covariates, numpy nanmean / nanstd): parity of the xarray glue itself is unpinned.
 Only outputs and the small inputs are stored; the large inputs are regenerated from the seeds by the tests
 (`inputs_c1` / `inputs_c2` below are imported by them).
 """
@@ -45,6 +50,17 @@ def inputs_c2(n=10000):
     ca, cb = conus_cells(2, n), conus_cells(3, n)
     va, vb = np.random.default_rng(5).standard_normal(n), np.random.default_rng(6).standard_normal(n)
     return [ca, cb], [va, vb]
+
+
+def inputs_preprocess():
+    rng = np.random.default_rng(21)
+    T, nla, nlo = 9, 6, 7
+    lat, lon = np.linspace(30.0, 35.0, nla), np.linspace(-100.0, -94.0, nlo)
+    cube = rng.standard_normal((T, nla, nlo)) + 0.3 * np.arange(T)[:, None, None] + 0.2 * lat[None, :, None] \
+        - 0.1 * lon[None, None, :]
+    cube[rng.uniform(size=cube.shape) < 0.15] = np.nan
+    cube[5] = np.nan  # one month without any data
+    return cube, lat, lon, 3
 
 
 def main():
@@ -104,6 +120,40 @@ def main():
             outc[f"{kind.lower()}_dist{i}{j}"] = cl["distance"].values
             outc[f"{kind.lower()}_cloud{i}{j}"] = cl["variogram"].values
     np.savez_compressed(os.path.join(HERE, "variogram_cloud.npz"), **outc)
+
+    # ------------------------------------------------------------------ preprocessing chain (numeric steps of the reference)
+    from sklearn.linear_model import LinearRegression
+    cube, lat, lon, ti = inputs_preprocess()
+    # fit_linear_trend (fields.py:283-287): mean over (lat, lon) per time step, then the reference's own regression helper
+    trend = ref.stat_tools.simple_linear_regression(np.nanmean(cube.reshape(len(cube), -1), axis=1))
+    field = (cube - trend[:, None, None])[ti]                                   # _preprocess_ds :352-356
+    LON, LAT = np.meshgrid(lon, lat, indexing="ij")
+    df = pd.DataFrame({"lon": LON.ravel(), "lat": LAT.ravel(), "v": field.T.ravel()}).dropna(subset=["v"]).reset_index(drop=True)
+    means = df[["lon", "lat"]].mean(axis=0, skipna=True).values                 # fit_ols :301-305
+    scales = df[["lon", "lat"]].std(axis=0, skipna=True).values
+    cov = df[["lon", "lat"]].copy()
+    for i, c in enumerate(["lon", "lat"]):
+        cov[c] = (cov[c] - means[i]) / scales[i]
+    model = LinearRegression().fit(cov, df["v"])
+    ols = model.predict(cov)
+    resid = df["v"].values - ols                                                # :366
+    mean, scale = np.nanmean(resid), np.nanstd(resid)                           # :369-370
+    std_vals = (resid - mean) / scale
+    # _postprocess_predictions (joint_prediction.py:155-205) on made-up standardised predictions at 5 locations
+    ploc = pd.DataFrame({"lat": [30.5, 31.5, 33.0, 34.5, 32.2], "lon": [-99.5, -97.0, -95.5, -94.2, -98.8],
+                         "pred": [0.3, -1.2, 0.8, 0.05, -0.4], "pred_err": [0.5, 0.7, 0.2, 0.9, 0.6]})
+    pc = ploc[["lon", "lat"]].copy()
+    for i, c in enumerate(["lon", "lat"]):
+        pc[c] = (pc[c] - means[i]) / scales[i]
+    back_pred = ploc["pred"].values * scale + mean + model.predict(pc) + trend[ti]
+    back_err = ploc["pred_err"].values * scale
+    np.savez_compressed(os.path.join(HERE, "preprocess.npz"), trend=trend, lon=df["lon"].values, lat=df["lat"].values,
+                        standardised=std_vals, spatial_trend=ols, covariate_means=means, covariate_scales=scales,
+                        spatial_mean=mean, scale_fact=scale, coef=model.coef_, intercept=model.intercept_,
+                        p_lat=ploc["lat"].values, p_lon=ploc["lon"].values, p_pred=ploc["pred"].values,
+                        p_err=ploc["pred_err"].values, back_pred=back_pred, back_err=back_err)
+    if os.environ.get("CK_GOLDEN_ONLY") == "preprocess":
+        return
 
     # ------------------------------------------------------------------ C2 at size
     coords, values = inputs_c2()

@@ -5,7 +5,7 @@ import numpy as np
 import pandas as pd
 import pytest
 
-from conftest import golden
+from conftest import GOLDEN, golden
 
 
 def test_matern_params_api_matches_reference_fixture():
@@ -206,3 +206,49 @@ def test_bench_reference_arm_line_contract():
     r1 = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2"], capture_output=True,
                         text=True, env=env, timeout=120)
     assert r1.returncode == 0 and r1.stdout.strip() == ""
+
+
+def test_preprocessing_and_back_transform_without_xarray():
+    """the reference's preprocessing chain (src/fields.py:283-375) and back-transform
+    (src/joint_prediction.py:155-205) on plain arrays, against the fixture tests/golden/make_golden_r2.py builds from the
+    reference's numeric steps (its own simple_linear_regression + the same sklearn / numpy calls)."""
+    import sys
+    import pandas as pd
+    sys.path.insert(0, GOLDEN)
+    from make_golden_r2 import inputs_preprocess
+    import fields
+    import joint_prediction
+    g = golden("preprocess")
+    cube, lat, lon, ti = inputs_preprocess()
+    np.testing.assert_allclose(fields.fit_linear_trend_array(cube), g["trend"], rtol=1e-13, equal_nan=True)
+    pre = fields.preprocess_arrays(cube, lat, lon, ti)
+    fr = pre["frame"].dropna(subset=["value"])
+    np.testing.assert_array_equal(fr["lon"].values, g["lon"])  # (lon, lat) row order of a (lon, lat, time) dataset
+    np.testing.assert_array_equal(fr["lat"].values, g["lat"])
+    np.testing.assert_allclose(fr["value"].values, g["standardised"], rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(fr["spatial_trend"].values, g["spatial_trend"], rtol=1e-12)
+    a = pre["attrs"]
+    np.testing.assert_allclose(a["covariate_means"], g["covariate_means"], rtol=1e-14)
+    np.testing.assert_allclose(a["covariate_scales"], g["covariate_scales"], rtol=1e-14)
+    assert abs(a["spatial_mean"] - g["spatial_mean"]) < 1e-14 and abs(a["scale_fact"] / g["scale_fact"] - 1) < 1e-13
+    assert abs(a["temporal_trend"] - g["trend"][ti]) < 1e-13
+    # Field / MultiField built from the cube, then the back-transform of standardised predictions
+    mf = fields.MultiField.from_cubes([cube, cube], [lat, lat], [lon, lon], [ti, ti])
+    f = mf.fields[0]
+    assert mf.n_procs == 2 and f.size == len(g["lon"]) and f.coords.shape == (f.size, 2)
+    np.testing.assert_array_equal(f.coords[:, 0], g["lat"])
+    np.testing.assert_allclose(f.values, g["standardised"], rtol=1e-12, atol=1e-13)
+    assert abs(np.mean(f.values)) < 1e-12 and abs(np.std(f.values) - 1) < 1e-12
+    P = object.__new__(joint_prediction.Predictor)
+    P.mf, P.i, P.covariates = mf, 0, None
+    back = P.postprocess_frame(pd.DataFrame({"lat": g["p_lat"], "lon": g["p_lon"], "pred": g["p_pred"], "pred_err": g["p_err"]}))
+    np.testing.assert_allclose(back["pred"].values, g["back_pred"], rtol=1e-12)
+    np.testing.assert_allclose(back["pred_err"].values, g["back_err"], rtol=1e-14)
+    # round trip: back-transforming the standardised data at the data locations returns the original slice
+    rt = P.postprocess_frame(pd.DataFrame({"lat": f.coords[:, 0], "lon": f.coords[:, 1], "pred": f.values, "pred_err": 0 * f.values}))
+    orig = pd.DataFrame({"lon": np.repeat(lon, len(lat)), "lat": np.tile(lat, len(lon)), "v": cube[ti].T.ravel()}).dropna()
+    np.testing.assert_allclose(rt["pred"].values, orig["v"].values, rtol=1e-12)
+    # a covariate given as an array instead of lon / lat
+    elev = np.add.outer(lat, -0.5 * lon)
+    pre2 = fields.preprocess_arrays(cube, lat, lon, ti, {"elev": elev})
+    assert pre2["covariate_names"] == ["elev"] and pre2["attrs"]["spatial_model"].coef_.shape == (1,)
