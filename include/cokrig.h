@@ -241,6 +241,18 @@ int ck_local_predict(const double* xy0_dev, const double* z0_dev, ck_i64 n0, con
 int ck_local_debug_buffer(void* dev_counters);
 
 /* ------------------------------------------------------------------------------------------------
+ * Temporal cross-correlation: src/stat_tools.py:128-160 compute_xcor_nd for EVERY lag of `lags` in one
+ * pass over two (ncell x T) row-major arrays (NaN = missing), optionally preceded by the per-cell linear detrend of
+ * apply_detrend (:56-75), plus the arg-max over lags of optim_lag_nd (:181-233).  numpy.ma semantics: Python-slice lag
+ * windows (negative lags included), sum(XY) over jointly valid entries, sum(XX) / sum(YY) over each series' own valid
+ * entries; NaN for fewer than tau joint entries (tau > 0), empty support or zero denominator.
+ * xcor_dev: nlag x ncell; best_idx_dev / best_xcor_dev (optional): index into `lags` of the largest |xcor| (0 if all NaN)
+ * and its value.  lags: HOST array, at most 64 entries.
+ * ---------------------------------------------------------------------------------------------- */
+int ck_xcor_lags(const double* z1_dev, const double* z2_dev, ck_i64 ncell, int t_len, const int* lags /*HOST*/, int nlag,
+                 int tau, int detrend, double* xcor_dev, int* best_idx_dev, double* best_xcor_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Multi-GPU building blocks (one process per GPU; the collectives are NCCL broadcasts issued by the host
  * side, cokrig_b200/parallel.py).  The large system is the AUGMENTED array
  *     [ Sigma (N x N, lower tiles) ; C^T (targets x N) + z ]      square tiles of `tb` elements,

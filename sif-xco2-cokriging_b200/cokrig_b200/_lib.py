@@ -91,6 +91,7 @@ SIGNATURES = {
     "ck_vario_bin": (c_int, [_dp, _dp, c_int64, c_double, _dp, _dp, c_int64, c_double, c_int, c_int, c_int,
                              c_double, _hp, c_int, _dp, _dp, _dp, c_int64, _dp, _dp, c_void_p]),
     "ck_local_predict_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "ck_xcor_lags": (c_int, [_dp, _dp, c_int64, c_int, POINTER(c_int), c_int, c_int, c_int, _dp, _dp, _dp, c_void_p]),
     "ck_local_debug_buffer": (c_int, [_dp]),
     "ck_local_count": (c_int, [_dp, c_int64, _dp, c_int64, _dp, c_int64, c_int, c_int, c_int, c_double, c_int,
                                _dp, _dp, c_void_p]),

@@ -374,3 +374,27 @@ def local_predict(coords: Sequence[torch.Tensor], values: Sequence[torch.Tensor]
                                _ptr(k), _ptr(seg), kmax,
                                _ptr(pred), _ptr(sd), _ptr(info), _ptr(ws), _stream()), "ck_local_predict")
     return (pred[:m].cpu().numpy(), sd[:m].cpu().numpy(), k[:m].cpu().numpy(), info[:m].cpu().numpy())
+
+
+# ------------------------------------------------------------------------------------------------ temporal statistics
+def xcor_lags(Z1, Z2, lags, tau=None, detrend: bool = False):
+    """Masked cross-correlation along the last axis of two equal-shape arrays for every integer lag in `lags`, in one
+    device pass (src/stat_tools.py:128-160, :181-233).  Returns (xcor with shape (nlag,) + Z1.shape[:-1], index of the
+    lag with the largest |xcor| per cell, that xcor) as numpy arrays."""
+    dev = require_cuda()
+    a = np.ascontiguousarray(np.asarray(Z1, dtype=np.float64))
+    b = np.ascontiguousarray(np.asarray(Z2, dtype=np.float64))
+    if a.shape != b.shape or a.ndim < 1:
+        raise ValueError("Z1 and Z2 must have the same shape with time as the last axis")
+    lg = np.ascontiguousarray(np.asarray(list(lags), dtype=np.int32))
+    T = a.shape[-1]
+    ncell = int(a.size // max(T, 1))
+    ad, bd = to_device(a.reshape(ncell, T)), to_device(b.reshape(ncell, T))
+    xc = torch.empty((len(lg), ncell), dtype=F64, device=dev)
+    bi = torch.zeros(max(ncell, 1), dtype=torch.int32, device=dev)
+    bx = torch.empty(max(ncell, 1), dtype=F64, device=dev)
+    check(lib.ck_xcor_lags(_ptr(ad), _ptr(bd), ncell, T, lg.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), len(lg),
+                           int(tau) if tau else 0, int(bool(detrend)), _ptr(xc), _ptr(bi), _ptr(bx), _stream()), "ck_xcor_lags")
+    cell_shape = a.shape[:-1]
+    return (xc.cpu().numpy().reshape((len(lg),) + cell_shape), bi[:ncell].cpu().numpy().reshape(cell_shape),
+            bx[:ncell].cpu().numpy().reshape(cell_shape))

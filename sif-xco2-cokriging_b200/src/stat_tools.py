@@ -4,6 +4,10 @@ Same names and signatures as /root/reference/src/stat_tools.py:9-271.  These are
 reductions over <= ~300 time steps (counts, linear detrending, lagged cross-correlation): O(n) host
 work outside the cokriging hot path, kept as vectorised numpy.  The
 ``apply_*`` wrappers and ``optim_lag_nd`` / ``get_stats`` need xarray (imported lazily).
+
+Device counterparts on plain arrays (no xarray): ``xcor_lags_device`` evaluates ``compute_xcor_nd`` for a whole range of
+lags -- and ``optim_lag_arrays`` the detrend + per-lag cross-correlation + arg-max of ``optim_lag_nd`` -- in ONE streaming
+kernel launch over the (lon, lat, time) cubes (``ck_xcor_lags``) instead of one masked-array numpy pass per lag.
 """
 from __future__ import annotations
 
@@ -117,6 +121,22 @@ def optim_lag_nd(da1, da2, lag_bnds, tau=None):
     xcor = np.squeeze(np.take_along_axis(stack, np.expand_dims(optim_lag, axis=2), 2), axis=2)
     return xarray.Dataset({"optim_lag": (["lon", "lat"], optim_lag), "xcor": (["lon", "lat"], xcor)},
                           coords={"lon": da1.lon, "lat": da1.lat})
+
+
+def xcor_lags_device(Z1, Z2, lags, tau=None, detrend: bool = False):
+    """``compute_xcor_nd(Z1, Z2, lag, tau)`` for every lag of `lags` at once, on the device: array of shape
+    (len(lags), lon, lat).  detrend=True first removes each cell's linear index trend (``apply_detrend``)."""
+    from _backend import ops
+    return ops.xcor_lags(Z1, Z2, lags, tau=tau, detrend=detrend)[0]
+
+
+def optim_lag_arrays(Z1, Z2, lag_bnds, tau=None):
+    """``optim_lag_nd`` (:181-233) on plain (lon, lat, time) arrays: per cell the INDEX into ``np.arange(*lag_bnds)`` of
+    the lag with the largest |cross-correlation| of the detrended series (0 where every lag is NaN) and that
+    cross-correlation.  Returns (optim_lag, xcor) -- the two variables of the reference's Dataset."""
+    from _backend import ops
+    _, idx, val = ops.xcor_lags(Z1, Z2, np.arange(*lag_bnds), tau=tau, detrend=True)
+    return idx.astype(np.int64), val
 
 
 # -- wrappers --------------------------------------------------------------------------------------
