@@ -116,16 +116,27 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
+_THREAD_LIMITS = None
+
+
 def _all_host_threads() -> int:
     """Use every host core for BLAS / LAPACK even when the launcher (torchrun) exported OMP_NUM_THREADS=1."""
+    global _THREAD_LIMITS
     cores = os.cpu_count() or 1
     try:
         os.sched_setaffinity(0, range(cores))
     except (AttributeError, OSError):
         pass
+    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[var] = str(cores)  # for libraries that are loaded after this point
     try:
+        # the BLAS / LAPACK copies the CPU path uses must be LOADED before their thread pools can be resized:
+        # numpy's and scipy's bundled OpenBLAS read OMP_NUM_THREADS=1 when they were imported
+        import scipy.linalg  # noqa: F401
+        import scipy.special  # noqa: F401
+        import sklearn.metrics.pairwise  # noqa: F401
         import threadpoolctl
-        threadpoolctl.threadpool_limits(limits=cores)
+        _THREAD_LIMITS = threadpoolctl.threadpool_limits(limits=cores)  # kept alive: limits stay in force
     except Exception:  # noqa: BLE001
         pass
     return cores

@@ -202,6 +202,13 @@ def test_bench_reference_arm_line_contract():
     assert cb["kind"] == "port" and cb["cores"] == os.cpu_count() and cb["value"] == d["value"] == d["e2e"]["value"]
     assert cb["value_without_verify"] > cb["value"] and set(cb["scaled_phases_s"]) == {"assemble_s", "verify_s", "factor_s", "solve_s"}
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    # the BLAS / LAPACK thread pools really are resized (torchrun exports OMP_NUM_THREADS=1 before Python starts)
+    probe = ("import sys; sys.path.insert(0, %r); import bench, json, threadpoolctl; n = bench._all_host_threads(); "
+             "print(json.dumps([n] + [p['num_threads'] for p in threadpoolctl.threadpool_info() if p['user_api'] == 'blas']))" % root)
+    rp = subprocess.run([sys.executable, "-c", probe], capture_output=True, text=True, env=env, timeout=120)
+    assert rp.returncode == 0, rp.stderr[-2000:]
+    counts = json.loads(rp.stdout.strip().splitlines()[-1])
+    assert counts[0] == os.cpu_count() and len(counts) >= 2 and all(c == counts[0] for c in counts[1:]), counts
     env["RANK"] = "1"  # the other ranks exit 0 without work
     r1 = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2"], capture_output=True,
                         text=True, env=env, timeout=120)
