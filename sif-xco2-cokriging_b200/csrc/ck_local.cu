@@ -6,26 +6,28 @@
 //   ck_local_count_kernel    neighbour counts per target, split into the eight (process, scan segment) pieces that the
 //                            second kernel needs to compact the neighbours IN THE REFERENCE'S ORDER (process 0 then 1,
 //                            index order = the order of the boolean masks) without re-counting;
-//   ck_local_predict_kernel  persistent CTAs of 128 threads (up to 4 per SM, one target each, targets handed out by an
-//                            atomic counter):
-//     1. scan + ordered compaction.  A conservative bounding test (|dx|, |dy| for Euclid; latitude band and a
-//        longitude bound for haversine, margins 1e-12 / 1e-9 >> the rounding of the distance) rejects most data with
+//   ck_local_predict_kernel  persistent CTAs of 160 threads (3 per SM, one target each, targets handed out by an
+//                            atomic counter): FOUR UPDATE WARPS + ONE DIAGONAL-BLOCK WARP.
+//     1. scan + ordered compaction (update warps).  A conservative bounding test (|dx|, |dy| for Euclid; latitude band and
+//        a longitude bound for haversine, margins 1e-12 / 1e-9 >> the rounding of the distance) rejects most data with
 //        a handful of instructions; survivors get the reference-order distance (bit-identical Euclid, libm-level
-//        haversine), so the neighbour sets equal the reference's.  The kept points, their covariance with the target
-//        (c) and their data (z) go to shared memory.
+//        haversine), so the neighbour sets equal the reference's.  The kept points (or their joint-matrix indices), their
+//        covariance with the target (c) and their data (z) go to shared memory.
 //     2. LEFT-looking blocked Cholesky in 32-column block columns on the (kp + 2)-row array  [Sigma_loc ; c^T ; z^T]
-//        (kp = k rounded up to 32, identity padded).  For block column J and a 64-row tile:
+//        (kp = k rounded up to 32, identity padded).  For block column J and every 64-row tile:
 //            W = Sigma[tile, J] - L[tile, 0:J) L[J, 0:J)^T
-//        The Sigma entries are RE-COMPUTED from the coordinates straight into the FP64 DMMA accumulator registers
-//        (no k x k matrix is ever stored or gathered: the only array in memory is L itself, written once), the
-//        product is FP64 tensor-core DMMA (mma.sync m8n8k4) fed by a cp.async-staged pipeline from the L2-resident
-//        workspace slot of the CTA.  The 32 x 32 diagonal block is eliminated by one warp with register-resident
-//        rows and shuffles (pivot reciprocal by Newton, square roots off the chain), its inverse X_d formed by
-//        forward substitution, and the rows below become  P = W X_d^T  (DMMA again, skipping the zero half of X_d).
-//        Because c and z ride along as two extra rows, the sweep leaves v = L^-1 c and y = L^-1 z: no separate solve.
+//        The Sigma entries are gathered from the stored joint covariance or RE-COMPUTED from the coordinates straight
+//        into the FP64 DMMA accumulator registers (no k x k matrix is ever stored: the only array in memory is L itself);
+//        the product is FP64 tensor-core DMMA (mma.sync m8n8k4) fed by a cp.async-staged pipeline from the L2-resident
+//        workspace slot of the CTA.  The 32 x 32 diagonal block of W goes to shared memory, where the DIAG WARP eliminates
+//        it with register-resident rows and shuffles (pivot reciprocal by Newton, square roots off the chain) and forms
+//        X_d = L_d^-1 by forward substitution -- ~30 k cycles of dependent FP64 work that used to idle the other three
+//        warps at a barrier (a quarter of the CTA's time, profiles/r02_k4_variants_phases.log) and now overlaps the update
+//        warps' main loops over the remaining row tiles, whose W is parked in place in the factor array.  Once X_d is
+//        published (named barriers) every update warp turns the rows it parked into  P = W X_d^T  (DMMA, skipping the zero
+//        half of X_d).  Because c and z ride along as two extra rows, the sweep leaves v = L^-1 c and y = L^-1 z.
 //     3. pred = v . y,  sd = sqrt(max(c0 - v . v, 0))   (src/point_prediction.py:200-222); NaN for an empty or
 //        non-positive-definite neighbourhood like the reference.
-//   While one CTA sits in its latency-bound 32-column elimination the other CTAs of the SM keep the FP64 pipe busy.
 //
 // Matern evaluation: when the three blocks of the joint model share one closed-form order nu in {1/2, 3/2, 5/2, 7/2}
 // (every BASELINE config) the matrix entries use the branch-free polynomial path of K1 (<= 2 ulp per piece,
@@ -38,21 +40,21 @@ constexpr int LTM = 64;            // rows per tile
 constexpr int LK = 16;             // k-depth per pipeline stage
 constexpr int LLD = LK + 4;        // staging row stride (doubles): % 16 == 4 -> conflict-free DMMA fragment loads
 #ifndef CK_LOCAL_STAGES
-#define CK_LOCAL_STAGES 2
+#define CK_LOCAL_STAGES 3  // measured (profiles/r02_k4_shapes.log): 2..3 stages, 16 / 32 deep, 3 / 4 CTAs per SM all land within 4 %
 #endif
 constexpr int LSTG = CK_LOCAL_STAGES;  // pipeline stages
 constexpr int LWLD = LP + 4;       // row stride of the W tile and of X_d
-constexpr int L_THREADS = 128;
-constexpr int L_WARPS = L_THREADS / 32;
+constexpr int L_UPD_THREADS = 128;  // four update warps: scan, covariance entries, DMMA main loops, panel products
+constexpr int L_WARPS = L_UPD_THREADS / 32;
+constexpr int L_THREADS = L_UPD_THREADS + 32;  // + one warp that only factors the 32 x 32 diagonal blocks
 constexpr int L_STAGE_ELEMS = (LTM + LP) * LLD;
 constexpr int L_SMEM_KMAX = 2048;  // neighbour records live in shared memory up to this k, in the workspace beyond
 constexpr int L_FAST_NONE = -1;    // FAST template values: 0..3 closed-form nu (polynomial path), -1 generic, -2 gather
 constexpr int L_GATHER = -2;
 #ifndef CK_LOCAL_MIN_CTAS
-#define CK_LOCAL_MIN_CTAS 4
+#define CK_LOCAL_MIN_CTAS 3
 #endif
 constexpr int L_MIN_CTAS = CK_LOCAL_MIN_CTAS;  // CTAs per SM the register allocation is bounded for
-static_assert(LTM * LWLD <= LSTG * L_STAGE_ELEMS, "the W tile aliases the staging buffers");
 
 struct LocalArgs {
   const double* xy[2]; const double* z[2]; long long n[2];
@@ -184,7 +186,7 @@ __device__ __forceinline__ int local_scan_segment(const LocalArgs& g, const Loca
 }
 
 template <int METRIC>
-__global__ void __launch_bounds__(L_THREADS) ck_local_count_kernel(const __grid_constant__ LocalArgs g, int* __restrict__ kout, int* __restrict__ kseg) {
+__global__ void __launch_bounds__(L_UPD_THREADS) ck_local_count_kernel(const __grid_constant__ LocalArgs g, int* __restrict__ kout, int* __restrict__ kseg) {
   __shared__ int seg[2 * L_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (long long c = blockIdx.x; c < g.m; c += gridDim.x) {
@@ -244,8 +246,9 @@ __device__ __forceinline__ double local_entry(const LocalArgs& g, int i, int j, 
 }
 
 // 32 x 32 diagonal block (one warp; out of line so that its 64 + 64 registers of row / column state are allocated
-// separately from the tile code): Wt rows 0..31 hold the lower triangle of D on entry and L_d on exit (D = L_d L_d^T), Xd
-// receives X_d = L_d^-1 (explicit zeros above the diagonal).  Returns 0 or 1 + the first column whose pivot is not > 0.
+// separately from the tile code): Wt rows 0..31 hold the lower triangle of D on entry (D = L_d L_d^T) and, on exit,
+// Xd receives X_d = L_d^-1 (explicit zeros above the diagonal); Xd may be the same buffer as Wt.
+// Returns 0 or 1 + the first column whose pivot is not > 0.
 static __device__ __noinline__ int local_diag_block(double* Wt, double* Xd, double* rsd, int lane) {
   // ---- elimination, lane = row; a[kk] holds the UNSCALED column entry until column kk is finished: only 1 / d sits on
   // the pivot chain (approximate reciprocal + two Newton steps), the 32 square roots are taken after the loop
@@ -290,20 +293,27 @@ static __device__ __noinline__ int local_diag_block(double* Wt, double* Xd, doub
 #pragma unroll
     for (int i = kk + 1; i < LP; ++i) x[i] = fma(-Wt[i * LWLD + kk], x[kk], x[i]);
   }
+  __syncwarp();  // every read of L_d is complete before X_d overwrites the buffer
 #pragma unroll
   for (int i = 0; i < LP; ++i) Xd[i * LWLD + lane] = x[i];
   return first_bad;
 }
 
+// named barriers (id 0 = __syncthreads over all five warps)
+#define L_BAR_UPD 1  // the four update warps among themselves
+#define L_BAR_D 2    // update warps arrive: the diagonal block of this block column is in shared memory; the diag warp waits
+#define L_BAR_X 3    // the diag warp arrives: X_d is in shared memory; the update warps wait before their panel products
+__device__ __forceinline__ void l_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void l_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
 template <int METRIC, int FAST>
 __global__ void __launch_bounds__(L_THREADS, L_MIN_CTAS) ck_local_predict_kernel(const __grid_constant__ LocalArgs g) {
   extern __shared__ __align__(16) double lsm[];
-  double* stage = lsm;                                  // LSTG x (LTM + LP) x LLD; aliased by the W tile
-  double* Wt = lsm;                                     // LTM x LWLD
-  double* Xd = stage + LSTG * L_STAGE_ELEMS;            // LP x LWLD: (L_d^-1)[r][c]
+  double* stage = lsm;                                  // LSTG x (LTM + LP) x LLD
+  double* Xd = stage + LSTG * L_STAGE_ELEMS;            // LP x LWLD: the diagonal block D, then X_d = L_d^-1
   double* rsd = Xd + LP * LWLD;                         // 1 / L_d[k][k]
-  double* red = rsd + LP;                               // L_THREADS
-  double* pts_sm = red + L_THREADS;
+  double* red = rsd + LP;                               // L_UPD_THREADS
+  double* pts_sm = red + L_UPD_THREADS;
   __shared__ int s_next, s_fail;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g4 = lane >> 2, t4 = lane & 3;
@@ -315,6 +325,7 @@ __global__ void __launch_bounds__(L_THREADS, L_MIN_CTAS) ck_local_predict_kernel
   double *pa = pbase, *pb = pa + kcap, *pcv = (FAST == L_GATHER) ? pa + kcap / 2 : pb + kcap, *pzv = pcv + kcap, *pc = pzv + kcap;
   const double qnan = __longlong_as_double(0x7FF8000000000000LL);
   const unsigned sbase = (unsigned)__cvta_generic_to_shared(stage);
+  const bool diag_warp = warp == L_WARPS;
 #ifdef CK_LOCAL_PROFILE  // phase counters (tools/k4_run.py --phases on a -DCK_LOCAL_PROFILE build); off in the product build
   long long tph[6] = {0, 0, 0, 0, 0, 0}, tlast = 0;
   const bool prof = g.dbg != nullptr && tid == 0;
@@ -342,6 +353,21 @@ __global__ void __launch_bounds__(L_THREADS, L_MIN_CTAS) ck_local_predict_kernel
       if (tid == 0) { g.pred[c] = qnan; g.sd[c] = qnan; g.info[c] = 0; }
       continue;
     }
+    const int kp = (k + LP - 1) / LP * LP, R = kp + 2;
+
+    if (diag_warp) {
+      // ===== the diagonal-block warp: per block column wait for D, eliminate, publish X_d.  Its ~30 k cycles of
+      // dependent FP64 work per block overlap the update warps' main loops of the remaining row tiles.
+      for (int c0 = 0; c0 < kp; c0 += LP) {
+        l_bar_sync(L_BAR_D, L_THREADS);
+        const int bad = local_diag_block(Xd, Xd, rsd, lane);
+        if (lane == 0 && bad != 0 && s_fail == 0) s_fail = c0 + bad;
+        l_bar_arrive(L_BAR_X, L_THREADS);
+      }
+      continue;  // joins the update warps at the __syncthreads of the next target
+    }
+
+    // ===== update warps
     // ---- 1. scan + ordered compaction (offsets from the eight segment counts of the first pass)
     int k0 = 0;
     {
@@ -358,24 +384,25 @@ __global__ void __launch_bounds__(L_THREADS, L_MIN_CTAS) ck_local_predict_kernel
       local_scan_segment<METRIC, true, FAST == L_GATHER>(g, f, p0, 0, warp, lane, off0, pa, pb, pc, pcv, pzv);
       if (g.n_procs == 2) local_scan_segment<METRIC, true, FAST == L_GATHER>(g, f, p0, 1, warp, lane, k0 + off1, pa, pb, pc, pcv, pzv);
     }
-    __syncthreads();
+    l_bar_sync(L_BAR_UPD, L_UPD_THREADS);
     L_STAMP(0);
 
     // ---- 2. left-looking blocked Cholesky of [Sigma_loc ; c ; z]
-    const int kp = (k + LP - 1) / LP * LP, R = kp + 2;
     for (int c0 = 0; c0 < kp; c0 += LP) {
       const int ntile = (R - c0 + LTM - 1) / LTM;
       const int KT = c0 / LK;
+      // 2a. W = Sigma[tile, J] - L[tile, 0:J) L[J, 0:J)^T for every row tile of the block column.  The diagonal block goes
+      // to shared memory (for the diag warp), every other row is parked IN PLACE in the factor array; the panel products
+      // follow in 2b once X_d is there.
       for (int t = 0; t < ntile; ++t) {
         const int i0 = c0 + t * LTM;
         const int wrow = i0 + 16 * warp;  // first row of this warp's 16 x 32 piece
-        __syncthreads();                  // the previous tile's W (aliasing the staging buffers) has been consumed
         // operand loader: A = L[i0 : i0 + 64, 0 : c0), B = L[c0 : c0 + 32, 0 : c0); per stage 96 rows x 8 chunks of 16 B
         auto load_stage = [&](int s, int kt) {
           const unsigned dst0 = sbase + (unsigned)(s * L_STAGE_ELEMS * 8);
 #pragma unroll
-          for (int it = 0; it < (LTM + LP) * (LK / 2) / L_THREADS; ++it) {
-            const int idx = tid + it * L_THREADS, row = idx >> 3, ch = idx & 7;
+          for (int it = 0; it < (LTM + LP) * (LK / 2) / L_UPD_THREADS; ++it) {
+            const int idx = tid + it * L_UPD_THREADS, row = idx / (LK / 2), ch = idx % (LK / 2);
             const int grow = row < LTM ? i0 + row : c0 + (row - LTM);
             const unsigned on = (kt < KT && grow < R) ? 1u : 0u;
             l_cp_async16(dst0 + (unsigned)((row * LLD + ch * 2) * 8), Lw + (long long)(on ? grow : 0) * ld + kt * LK + ch * 2, on);
@@ -388,8 +415,8 @@ __global__ void __launch_bounds__(L_THREADS, L_MIN_CTAS) ck_local_predict_kernel
             l_cp_commit();
           }
         }
-        // accumulators start at -Sigma (so that W = -(acc + A B^T ...) needs no negated operand): entries re-computed from
-        // the coordinates while the first operand stage is in flight
+        // accumulators start at -Sigma (so that W = -(acc + A B^T ...) needs no negated operand): entries gathered /
+        // re-computed while the first operand stage is in flight
         double acc[2][4][2];
         const bool plain = (t > 0) && (i0 + LTM <= k);  // every row is a matrix row below the diagonal block
         // rows of the identity pad (k <= i < kp) stay e_i through the whole sweep and rows past R do not exist: a warp whose
@@ -416,7 +443,7 @@ __global__ void __launch_bounds__(L_THREADS, L_MIN_CTAS) ck_local_predict_kernel
           int rd = 0, wr = LSTG - 1;
           for (int kt = 0; kt < KT; ++kt) {
             l_cp_wait<LSTG - 2>();
-            __syncthreads();
+            l_bar_sync(L_BAR_UPD, L_UPD_THREADS);
             load_stage(wr, kt + LSTG - 1);
             l_cp_commit();
             const double* As = stage + rd * L_STAGE_ELEMS + (16 * warp + g4) * LLD + t4;
@@ -438,84 +465,99 @@ __global__ void __launch_bounds__(L_THREADS, L_MIN_CTAS) ck_local_predict_kernel
             wr = (wr + 1 == LSTG) ? 0 : wr + 1;
           }
           l_cp_wait<0>();
-          __syncthreads();  // every warp is done with the staging buffers: W may overwrite them
+          l_bar_sync(L_BAR_UPD, L_UPD_THREADS);  // every warp is done with the staging buffers: the next tile may refill them
         }
-        // W tile -> shared memory (A-operand layout of the panel product)
-#pragma unroll
-        for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-          for (int ni = 0; ni < 4; ++ni)
-            *reinterpret_cast<double2*>(Wt + (16 * warp + 8 * mi + g4) * LWLD + 8 * ni + 2 * t4) =
-                make_double2(-acc[mi][ni][0], -acc[mi][ni][1]);
         L_STAMP(2);
-        if (t == 0) {
-          __syncthreads();
-          if (warp == 0) {
-            const int bad = local_diag_block(Wt, Xd, rsd, lane);
-            if (lane == 0 && bad != 0 && s_fail == 0) s_fail = c0 + bad;
-          }
-          __syncthreads();
-          L_STAMP(3);
-        } else {
-          __syncwarp();
-        }
-        // ---- panel: P = W X_d^T for the rows below the diagonal block; column tile ni only needs k <= 8 ni + 7
-        if (t > 0 || warp >= 2) {
-          double out[2][4][2];
-          const double* Aw = Wt + (16 * warp + g4) * LWLD + t4;
+        // W: diagonal block -> shared memory (read by the diag warp), everything else -> parked in place
+        if (t == 0 && warp < 2) {
 #pragma unroll
           for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-            for (int ni = 0; ni < 4; ++ni) {
-              out[mi][ni][0] = 0.0;
-              out[mi][ni][1] = 0.0;
-            }
-#pragma unroll
-          for (int ks = 0; ks < LP / 4; ++ks) {
-            double a[2];
-#pragma unroll
-            for (int mi = 0; mi < 2; ++mi) a[mi] = Aw[mi * 8 * LWLD + 4 * ks];
-#pragma unroll
-            for (int ni = 0; ni < 4; ++ni) {
-              if (4 * ks > 8 * ni + 7) continue;  // X_d is lower triangular
-              const double b = Xd[(8 * ni + g4) * LWLD + 4 * ks + t4];
-#pragma unroll
-              for (int mi = 0; mi < 2; ++mi) l_dmma(out[mi][ni][0], out[mi][ni][1], a[mi], b);
-            }
-          }
+            for (int ni = 0; ni < 4; ++ni)
+              *reinterpret_cast<double2*>(Xd + (16 * warp + 8 * mi + g4) * LWLD + 8 * ni + 2 * t4) =
+                  make_double2(-acc[mi][ni][0], -acc[mi][ni][1]);
+        } else {
 #pragma unroll
           for (int mi = 0; mi < 2; ++mi) {
             const int i = wrow + 8 * mi + g4;
             if (i < R) {
               double* dst = Lw + (long long)i * ld + c0 + 2 * t4;
 #pragma unroll
-              for (int ni = 0; ni < 4; ++ni) *reinterpret_cast<double2*>(dst + 8 * ni) = make_double2(out[mi][ni][0], out[mi][ni][1]);
+              for (int ni = 0; ni < 4; ++ni) *reinterpret_cast<double2*>(dst + 8 * ni) = make_double2(-acc[mi][ni][0], -acc[mi][ni][1]);
             }
           }
         }
-        L_STAMP(4);
+        if (t == 0) l_bar_arrive(L_BAR_D, L_THREADS);  // D is complete once all four update warps have arrived
       }
+      // 2b. panel products P = W X_d^T: every warp handles the rows it parked itself (same lanes' warp, so __syncwarp
+      // orders the global round trip); column tile ni only needs k <= 8 ni + 7 because X_d is lower triangular
+      l_bar_sync(L_BAR_X, L_THREADS);
+      L_STAMP(3);
+      __syncwarp();
+      for (int t = 0; t < ntile; ++t) {
+        if (t == 0 && warp < 2) continue;
+        const int wrow = c0 + t * LTM + 16 * warp;
+        if (wrow >= R) continue;
+        double out[2][4][2];
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < 4; ++ni) {
+            out[mi][ni][0] = 0.0;
+            out[mi][ni][1] = 0.0;
+          }
+        const int r0 = wrow + g4, r1 = wrow + 8 + g4;
+        const double* w0 = Lw + (long long)(r0 < R ? r0 : wrow) * ld + c0 + t4;
+        const double* w1 = Lw + (long long)(r1 < R ? r1 : wrow) * ld + c0 + t4;
+        double a0[LP / 4], a1[LP / 4];
+#pragma unroll
+        for (int ks = 0; ks < LP / 4; ++ks) {
+          a0[ks] = __ldcg(w0 + 4 * ks);
+          a1[ks] = __ldcg(w1 + 4 * ks);
+        }
+        __syncwarp();  // all fragments of the strip are in registers before any row of it is overwritten
+#pragma unroll
+        for (int ks = 0; ks < LP / 4; ++ks) {
+#pragma unroll
+          for (int ni = 0; ni < 4; ++ni) {
+            if (4 * ks > 8 * ni + 7) continue;  // X_d is lower triangular
+            const double b = Xd[(8 * ni + g4) * LWLD + 4 * ks + t4];
+            l_dmma(out[0][ni][0], out[0][ni][1], a0[ks], b);
+            l_dmma(out[1][ni][0], out[1][ni][1], a1[ks], b);
+          }
+        }
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi) {
+          const int i = wrow + 8 * mi + g4;
+          if (i < R) {
+            double* dst = Lw + (long long)i * ld + c0 + 2 * t4;
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) *reinterpret_cast<double2*>(dst + 8 * ni) = make_double2(out[mi][ni][0], out[mi][ni][1]);
+          }
+        }
+      }
+      l_bar_sync(L_BAR_UPD, L_UPD_THREADS);  // the block column of L is complete: the next one may stage it
+      L_STAMP(4);
     }
-    __syncthreads();
     // ---- 3. prediction: rows kp (v = L^-1 c) and kp + 1 (y = L^-1 z) of the factor array
     double sv = 0.0, sy = 0.0;
     {
       const double* vrow = Lw + (long long)kp * ld;
       const double* yrow = vrow + ld;
-      for (int b = tid; b < kp; b += L_THREADS) {
-        const double v = vrow[b], y = yrow[b];
+      for (int b = tid; b < kp; b += L_UPD_THREADS) {
+        const double v = __ldcg(vrow + b), y = __ldcg(yrow + b);
         sv = fma(v, v, sv);
         sy = fma(v, y, sy);
       }
     }
     red[tid] = sv;
-    __syncthreads();
-    for (int h = L_THREADS / 2; h > 0; h >>= 1) { if (tid < h) red[tid] += red[tid + h]; __syncthreads(); }
+    l_bar_sync(L_BAR_UPD, L_UPD_THREADS);
+    for (int h = L_UPD_THREADS / 2; h > 0; h >>= 1) { if (tid < h) red[tid] += red[tid + h]; l_bar_sync(L_BAR_UPD, L_UPD_THREADS); }
     sv = red[0];
-    __syncthreads();
+    l_bar_sync(L_BAR_UPD, L_UPD_THREADS);
     red[tid] = sy;
-    __syncthreads();
-    for (int h = L_THREADS / 2; h > 0; h >>= 1) { if (tid < h) red[tid] += red[tid + h]; __syncthreads(); }
+    l_bar_sync(L_BAR_UPD, L_UPD_THREADS);
+    for (int h = L_UPD_THREADS / 2; h > 0; h >>= 1) { if (tid < h) red[tid] += red[tid + h]; l_bar_sync(L_BAR_UPD, L_UPD_THREADS); }
     sy = red[0];
     if (tid == 0) {
       if (s_fail) {
@@ -583,7 +625,7 @@ static LocalPlan local_plan(ck_i64 m, ck_i64 kmax, int metric, bool gather = fal
   const long long rec = 5 * kcap;  // a, b, c-vector, z, cos(lat)
   p.slot_stride = (p.kmaxp + 2) * p.kmaxp + (p.pts_in_ws ? rec : 0);
   p.slot_stride = (p.slot_stride + 31) / 32 * 32;
-  long long slots = 148 * 4;
+  long long slots = 148 * L_MIN_CTAS;  // one slot per resident CTA
   const long long budget = (8LL << 30) / 8;  // at most 8 GB of factor slots
   if (slots * p.slot_stride > budget) slots = budget / p.slot_stride;
   if (slots < 148) slots = 148;
@@ -591,7 +633,7 @@ static LocalPlan local_plan(ck_i64 m, ck_i64 kmax, int metric, bool gather = fal
   p.slots = slots;
   const long long narr = (metric == CK_METRIC_HAVERSINE) ? 5 : 4;
   const long long recs = gather ? kcap / 2 + 2 * kcap : narr * kcap;
-  p.smem = (size_t)(LSTG * L_STAGE_ELEMS + LP * LWLD + LP + L_THREADS + (p.pts_in_ws ? 0 : recs)) * sizeof(double);
+  p.smem = (size_t)(LSTG * L_STAGE_ELEMS + LP * LWLD + LP + L_UPD_THREADS + (p.pts_in_ws ? 0 : recs)) * sizeof(double);
   return p;
 }
 
@@ -625,8 +667,8 @@ extern "C" int ck_local_count(const double* xy0, ck_i64 n0, const double* xy1, c
   CK_REQUIRE((((uintptr_t)xy0 | (uintptr_t)xy1) & 15) == 0, "coordinate arrays must be 16-byte aligned");
   const unsigned grid = (unsigned)(m < 148 * 16 ? m : 148 * 16);
   cudaStream_t st = ck_stream(stream);
-  if (metric == CK_METRIC_HAVERSINE) ck_local_count_kernel<CK_METRIC_HAVERSINE><<<grid, L_THREADS, 0, st>>>(g, k_dev, seg_dev);
-  else ck_local_count_kernel<CK_METRIC_EUCLID><<<grid, L_THREADS, 0, st>>>(g, k_dev, seg_dev);
+  if (metric == CK_METRIC_HAVERSINE) ck_local_count_kernel<CK_METRIC_HAVERSINE><<<grid, L_UPD_THREADS, 0, st>>>(g, k_dev, seg_dev);
+  else ck_local_count_kernel<CK_METRIC_EUCLID><<<grid, L_UPD_THREADS, 0, st>>>(g, k_dev, seg_dev);
   CK_LAUNCH_CHECK();
   return CK_OK;
 }
