@@ -77,9 +77,117 @@ struct K1Point<CK_METRIC_HAVERSINE, 1> {
   static __device__ __forceinline__ double dist(const type& p, const type& q) { return ck_dist_haversine_pre(p, q); }
 };
 
+
+// ------------------------------------------------------------------------------------------------
+// Closed-form covariance blocks: the 16 entries of a thread are evaluated in two groups of eight with WARP-UNIFORM fast
+// paths.  Round-2 ncu (profiles/r02_k1_ncu_full_summary.txt) showed the branch-free scalar path issue-bound: 186
+// instructions per entry of which only 71 on the FP64 pipe -- the rest FSEL pairs of the branch-free selects, register
+// moves and one uniform-datapath coefficient load per polynomial term per entry.  Here (a) every polynomial is evaluated
+// coefficient-major over the eight entries, so a coefficient is fetched once per eight Horner steps, and (b) when a vote
+// shows that every lane's eight entries are in the common range (haversine a <= 1/4, i.e. pairs closer than ~6 670 km;
+// 0 < x < the kv underflow cut-off) the selects disappear; any lane outside it sends the whole warp through the general
+// scalar functions of ck_math.cuh (diagonal tiles, coincident points, antipodal pairs).  Same arithmetic per entry in
+// both paths: ck_fast_sqrt, the same polynomials, the same exponent insertion.
+// ------------------------------------------------------------------------------------------------
+constexpr unsigned K1_FULL = 0xffffffffu;
+
+// d[e] = 2 R asin(sqrt(a[e])) for eight values of the haversine argument
+__device__ __forceinline__ void k1_asin8(const double (&a)[8], double (&d)[8]) {
+  bool small = true;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) small &= a[e] <= 0.25;
+  if (__all_sync(K1_FULL, small)) {  // asin(sqrt(a)) = sqrt(a) (1 + a R(a))
+    double r[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) r[e] = CK_COEF(asin_r, 12);
+#pragma unroll
+    for (int i = 11; i >= 0; --i) {
+      const double c = CK_COEF(asin_r, i);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) r[e] = fma(r[e], a[e], c);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) d[e] = (ck_fast_sqrt(a[e]) * (2.0 * CK_EARTH_RADIUS)) * fma(a[e], r[e], 1.0);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) d[e] = ck_fast_asin_sqrt(a[e]) * (2.0 * CK_EARTH_RADIUS);
+  }
+}
+
+// out[e] = sigma^2 rho(h[e]) (+ nugget where h == 0) for eight distances, closed-form orders
+template <int MODE>
+__device__ __forceinline__ void k1_matern8(const CkMatern& P, const double (&h)[8], double (&out)[8]) {
+  const double xlim = P.x_cut < 705.0 ? P.x_cut : 705.0;
+  double x[8];
+  bool plain = true;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    x[e] = fabs(h[e]) * P.xscale;
+    plain &= (x[e] > 0.0) & (x[e] < xlim);
+  }
+  if (__all_sync(K1_FULL, plain)) {
+    const double magic = 6755399441055744.0;  // 1.5 * 2^52, see ck_fast_exp_neg
+    double t[8], r[8], q[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      t[e] = fma(x[e], -1.4426950408889634074, magic);
+      const double nf = t[e] - magic;
+      r[e] = fma(nf, -6.93147180369123816490e-01, -x[e]);
+      r[e] = fma(nf, -1.90821492927058770002e-10, r[e]);
+      q[e] = CK_COEF(exp_e, 9);
+    }
+#pragma unroll
+    for (int i = 8; i >= 0; --i) {
+      const double c = CK_COEF(exp_e, i);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) q[e] = fma(q[e], r[e], c);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const double p = fma(r[e] * r[e], q[e], r[e]) + 1.0;
+      const double ex = __hiloint2double(__double2hiint(p) + (__double2loint(t[e]) << 20), __double2loint(p));
+      double poly;
+      if (MODE == CK_NU_HALF) poly = 1.0;
+      else if (MODE == CK_NU_3HALF) poly = 1.0 + x[e];
+      else if (MODE == CK_NU_5HALF) poly = fma(x[e], fma(x[e], 1.0 / 3.0, 1.0), 1.0);
+      else poly = fma(x[e], fma(x[e], fma(x[e], 1.0 / 15.0, 0.4), 1.0), 1.0);
+      out[e] = P.scale * (poly * ex);
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) out[e] = ck_matern_cov_fast<MODE>(P, h[e]);
+  }
+}
+
+// eight pair distances of one column point q against the thread's eight row points
+template <int METRIC>
+struct K1Dist8;
+template <>
+struct K1Dist8<CK_METRIC_HAVERSINE> {
+  static __device__ __forceinline__ void run(const CkPointH* pr, int ty, const CkPointH& q, double (&h)[8]) {
+    double a[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const CkPointH p = pr[ty + 8 * r];
+      const double s0 = __dsub_rn(__dmul_rn(p.sa, q.ca), __dmul_rn(p.ca, q.sa));
+      const double s1 = __dsub_rn(__dmul_rn(p.sb, q.cb), __dmul_rn(p.cb, q.sb));
+      a[r] = fma(p.c * q.c, s1 * s1, s0 * s0);
+    }
+    k1_asin8(a, h);
+  }
+};
+template <>
+struct K1Dist8<CK_METRIC_EUCLID> {
+  static __device__ __forceinline__ void run(const CkPoint* pr, int ty, const CkPoint& q, double (&h)[8]) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) h[r] = ck_dist_euclid_fast(pr[ty + 8 * r], q);
+  }
+};
+
 // VALUE: 0 = distance only, 1 = covariance
 template <int METRIC, int MODE, int VALUE>
-__global__ void __launch_bounds__(K1_THREADS, (MODE == CK_NU_GENERIC && VALUE) ? 2 : 4) ck_block_kernel(const double* __restrict__ xy1, long long n1,
+__global__ void __launch_bounds__(K1_THREADS, (MODE == CK_NU_GENERIC && VALUE) ? 2 : ((METRIC == CK_METRIC_HAVERSINE && VALUE) ? 3 : 4))
+    ck_block_kernel(const double* __restrict__ xy1, long long n1,
                                                               const double* __restrict__ xy2, long long n2,
                                                               CkMatern P, double* __restrict__ out, long long ld,
                                                               double* __restrict__ out_t, long long ld_t,
@@ -91,41 +199,45 @@ __global__ void __launch_bounds__(K1_THREADS, (MODE == CK_NU_GENERIC && VALUE) ?
   __shared__ double tr[TILE][TILE + 1];
   const int t = threadIdx.x;
   const long long r0 = bi * TILE, c0 = bj * TILE;
-  if (t < TILE) {
-    const long long r = r0 + t;
-    if (r < n1) pr[t] = PT::prepare(xy1[2 * r], xy1[2 * r + 1]);
+  if (t < TILE) {  // points past the end of the block are staged as copies of its last point: never stored, but every
+    const long long r = (r0 + t < n1) ? r0 + t : n1 - 1;  // lane computes on valid data and takes part in the warp votes
+    pr[t] = PT::prepare(xy1[2 * r], xy1[2 * r + 1]);
   } else if (t < 2 * TILE) {
-    const long long c = c0 + (t - TILE);
-    if (c < n2) pc[t - TILE] = PT::prepare(xy2[2 * c], xy2[2 * c + 1]);
+    const long long c = (c0 + (t - TILE) < n2) ? c0 + (t - TILE) : n2 - 1;
+    pc[t - TILE] = PT::prepare(xy2[2 * c], xy2[2 * c + 1]);
   }
   __syncthreads();
   const int tx = t & 31, ty = t >> 5;  // 8 warps; warp `ty` owns rows ty, ty+8, ...
   const bool mirror = (out_t != nullptr) && !(symmetric && bi == bj);
-  double v[8][2];
-#pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    const int lr = ty + 8 * r;
+  if constexpr (VALUE != 0 && MODE != CK_NU_GENERIC) {
+    // closed-form orders: two groups of eight entries (one column point each) through the warp-uniform fast paths;
+    // each group is stored as soon as it is finished (eight results live, not sixteen)
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       const int lc = tx + 32 * c;
-      double val = 0.0;
-      if (r0 + lr < n1 && c0 + lc < n2) {
-        const double h = PT::dist(pr[lr], pc[lc]);
-        if (VALUE && MODE != CK_NU_GENERIC) val = ck_matern_cov_fast<MODE>(P, h);  // closed-form orders: branch-free fast math
-        else if (VALUE) val = ck_matern_cov<MODE>(P, h);                          // generic order: K_nu by series / Chebyshev fits
-        else val = h;                                                             // distance output: reference operation order
+      double h[8], o[8];
+      K1Dist8<METRIC>::run(pr, ty, pc[lc], h);
+      k1_matern8<MODE>(P, h, o);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int lr = ty + 8 * r;
+        if (r0 + lr < n1 && c0 + lc < n2) out[(r0 + lr) * ld + (c0 + lc)] = o[r];
+        if (mirror) tr[lr][lc] = o[r];
       }
-      v[r][c] = val;
     }
-  }
+  } else {
 #pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    const int lr = ty + 8 * r;
+    for (int r = 0; r < 8; ++r) {
+      const int lr = ty + 8 * r;
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      const int lc = tx + 32 * c;
-      if (r0 + lr < n1 && c0 + lc < n2) out[(r0 + lr) * ld + (c0 + lc)] = v[r][c];
-      if (mirror) tr[lr][lc] = v[r][c];
+      for (int c = 0; c < 2; ++c) {
+        const int lc = tx + 32 * c;
+        const double h = PT::dist(pr[lr], pc[lc]);
+        const double val = VALUE ? ck_matern_cov<MODE>(P, h)  // generic order: K_nu by series / Chebyshev fits
+                                 : h;                         // distance output: reference operation order
+        if (r0 + lr < n1 && c0 + lc < n2) out[(r0 + lr) * ld + (c0 + lc)] = val;
+        if (mirror) tr[lr][lc] = val;
+      }
     }
   }
   if (mirror) {
