@@ -32,11 +32,14 @@ F64 = torch.float64
 
 # ------------------------------------------------------------------------------------------------ grid
 def grid_shape(world: int) -> Tuple[int, int]:
-    """P x Q process grid for `world` ranks: as square as possible with P <= Q (8 -> 2 x 4)."""
-    p = int(np.floor(np.sqrt(world)))
-    while world % p:
-        p -= 1
-    return p, world // p
+    """P x Q process grid for `world` ranks: as square as possible with P >= Q (2 -> 2 x 1, 4 -> 2 x 2, 8 -> 4 x 2).
+    More process ROWS split the panel work (column update + TRSM product of every tile column, the critical path of
+    the sweep) over more ranks; measured on C3: 2 x 1 250 ms vs 1 x 2 261 ms, 4 x 2 103 ms vs 2 x 4 114 ms
+    (profiles/r02_mg_c3_*gpu_grid_shapes.log)."""
+    q = int(np.floor(np.sqrt(world)))
+    while world % q:
+        q -= 1
+    return world // q, q
 
 
 class ProcessGrid:

@@ -115,8 +115,8 @@ def test_vario_split_balances_active_tiles():
 
 def test_grid_shape_and_tile_ownership():
     from cokrig_b200 import parallel
-    assert parallel.grid_shape(8) == (2, 4) and parallel.grid_shape(4) == (2, 2)
-    assert parallel.grid_shape(2) == (1, 2) and parallel.grid_shape(1) == (1, 1)
+    assert parallel.grid_shape(8) == (4, 2) and parallel.grid_shape(4) == (2, 2)
+    assert parallel.grid_shape(2) == (2, 1) and parallel.grid_shape(1) == (1, 1)
     for ntiles in (0, 1, 5, 8, 13):
         for nprocs in (1, 2, 3, 4):
             owned = [parallel.local_tiles(ntiles, nprocs, r) for r in range(nprocs)]
