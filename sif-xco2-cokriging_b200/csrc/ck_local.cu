@@ -36,7 +36,12 @@
 #include "ck_common.cuh"
 
 constexpr int LP = 32;             // block-column (panel) width
-constexpr int LTM = 64;            // rows per tile
+#ifndef CK_LOCAL_TM
+#define CK_LOCAL_TM 64
+#endif
+constexpr int LTM = CK_LOCAL_TM;   // rows per tile (64 or 128)
+constexpr int LWR = LTM / 4;       // rows per update warp (16 or 32)
+constexpr int LMI = LWR / 8;       // 8-row DMMA tiles per warp
 constexpr int LK = 16;             // k-depth per pipeline stage
 constexpr int LLD = LK + 4;        // staging row stride (doubles): % 16 == 4 -> conflict-free DMMA fragment loads
 #ifndef CK_LOCAL_STAGES
@@ -396,7 +401,7 @@ __global__ void __launch_bounds__(L_THREADS, L_MIN_CTAS) ck_local_predict_kernel
       // follow in 2b once X_d is there.
       for (int t = 0; t < ntile; ++t) {
         const int i0 = c0 + t * LTM;
-        const int wrow = i0 + 16 * warp;  // first row of this warp's 16 x 32 piece
+        const int wrow = i0 + LWR * warp;  // first row of this warp's LWR x 32 piece
         // operand loader: A = L[i0 : i0 + 64, 0 : c0), B = L[c0 : c0 + 32, 0 : c0); per stage 96 rows x 8 chunks of 16 B
         auto load_stage = [&](int s, int kt) {
           const unsigned dst0 = sbase + (unsigned)(s * L_STAGE_ELEMS * 8);
@@ -417,17 +422,17 @@ __global__ void __launch_bounds__(L_THREADS, L_MIN_CTAS) ck_local_predict_kernel
         }
         // accumulators start at -Sigma (so that W = -(acc + A B^T ...) needs no negated operand): entries gathered /
         // re-computed while the first operand stage is in flight
-        double acc[2][4][2];
+        double acc[LMI][4][2];
         const bool plain = (t > 0) && (i0 + LTM <= k);  // every row is a matrix row below the diagonal block
         // rows of the identity pad (k <= i < kp) stay e_i through the whole sweep and rows past R do not exist: a warp whose
         // 16 rows are all of that kind issues no DMMA (it still takes part in the operand staging and the barriers)
 #ifdef CK_LOCAL_NO_SKIP
         const bool live = true;
 #else
-        const bool live = wrow < R && !(wrow >= k && wrow + 16 <= kp);
+        const bool live = wrow < R && !(wrow >= k && wrow + LWR <= kp);
 #endif
 #pragma unroll
-        for (int mi = 0; mi < 2; ++mi)
+        for (int mi = 0; mi < LMI; ++mi)
 #pragma unroll
           for (int ni = 0; ni < 4; ++ni)
 #pragma unroll
@@ -446,18 +451,18 @@ __global__ void __launch_bounds__(L_THREADS, L_MIN_CTAS) ck_local_predict_kernel
             l_bar_sync(L_BAR_UPD, L_UPD_THREADS);
             load_stage(wr, kt + LSTG - 1);
             l_cp_commit();
-            const double* As = stage + rd * L_STAGE_ELEMS + (16 * warp + g4) * LLD + t4;
+            const double* As = stage + rd * L_STAGE_ELEMS + (LWR * warp + g4) * LLD + t4;
             const double* Bs = stage + rd * L_STAGE_ELEMS + (LTM + g4) * LLD + t4;
             if (live)
 #pragma unroll
             for (int kk = 0; kk < LK; kk += 4) {
-              double a[2], b[4];
+              double a[LMI], b[4];
 #pragma unroll
-              for (int mi = 0; mi < 2; ++mi) a[mi] = As[mi * 8 * LLD + kk];
+              for (int mi = 0; mi < LMI; ++mi) a[mi] = As[mi * 8 * LLD + kk];
 #pragma unroll
               for (int ni = 0; ni < 4; ++ni) b[ni] = Bs[ni * 8 * LLD + kk];
 #pragma unroll
-              for (int mi = 0; mi < 2; ++mi)
+              for (int mi = 0; mi < LMI; ++mi)
 #pragma unroll
                 for (int ni = 0; ni < 4; ++ni) l_dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
             }
@@ -469,16 +474,16 @@ __global__ void __launch_bounds__(L_THREADS, L_MIN_CTAS) ck_local_predict_kernel
         }
         L_STAMP(2);
         // W: diagonal block -> shared memory (read by the diag warp), everything else -> parked in place
-        if (t == 0 && warp < 2) {
+        if (t == 0 && warp < LP / LWR) {
 #pragma unroll
-          for (int mi = 0; mi < 2; ++mi)
+          for (int mi = 0; mi < LMI; ++mi)
 #pragma unroll
             for (int ni = 0; ni < 4; ++ni)
-              *reinterpret_cast<double2*>(Xd + (16 * warp + 8 * mi + g4) * LWLD + 8 * ni + 2 * t4) =
+              *reinterpret_cast<double2*>(Xd + (LWR * warp + 8 * mi + g4) * LWLD + 8 * ni + 2 * t4) =
                   make_double2(-acc[mi][ni][0], -acc[mi][ni][1]);
         } else {
 #pragma unroll
-          for (int mi = 0; mi < 2; ++mi) {
+          for (int mi = 0; mi < LMI; ++mi) {
             const int i = wrow + 8 * mi + g4;
             if (i < R) {
               double* dst = Lw + (long long)i * ld + c0 + 2 * t4;
@@ -494,9 +499,10 @@ __global__ void __launch_bounds__(L_THREADS, L_MIN_CTAS) ck_local_predict_kernel
       l_bar_sync(L_BAR_X, L_THREADS);
       L_STAMP(3);
       __syncwarp();
-      for (int t = 0; t < ntile; ++t) {
-        if (t == 0 && warp < 2) continue;
-        const int wrow = c0 + t * LTM + 16 * warp;
+      for (int ts = 0; ts < ntile * (LWR / 16); ++ts) {
+        const int t = ts / (LWR / 16);
+        if (t == 0 && warp < LP / LWR) continue;
+        const int wrow = c0 + t * LTM + LWR * warp + 16 * (ts % (LWR / 16));  // 16-row strips of the rows this warp parked
         if (wrow >= R) continue;
         double out[2][4][2];
 #pragma unroll
