@@ -184,14 +184,23 @@ struct K1Dist8<CK_METRIC_EUCLID> {
   }
 };
 
+// kernel argument that carries the generic-nu correlation table only for the instantiations that use it
+template <bool TAB>
+struct K1TabArg {
+  CkMaternTable T;
+};
+template <>
+struct K1TabArg<false> {};
+
 // VALUE: 0 = distance only, 1 = covariance
 template <int METRIC, int MODE, int VALUE>
-__global__ void __launch_bounds__(K1_THREADS, (MODE == CK_NU_GENERIC && VALUE) ? 2 : ((METRIC == CK_METRIC_HAVERSINE && VALUE) ? 3 : 4))
+__global__ void __launch_bounds__(K1_THREADS, (METRIC == CK_METRIC_HAVERSINE && VALUE) ? 3 : 4)
     ck_block_kernel(const double* __restrict__ xy1, long long n1,
                                                               const double* __restrict__ xy2, long long n2,
                                                               CkMatern P, double* __restrict__ out, long long ld,
                                                               double* __restrict__ out_t, long long ld_t,
-                                                              int symmetric) {
+                                                              int symmetric,
+                                                              const __grid_constant__ K1TabArg<(MODE == CK_NU_GENERIC && VALUE != 0)> tab) {
   const long long bi = blockIdx.y, bj = blockIdx.x;
   if (symmetric && bj < bi) return;  // mirrored from the upper tile
   using PT = K1Point<METRIC, VALUE>;
@@ -205,6 +214,12 @@ __global__ void __launch_bounds__(K1_THREADS, (MODE == CK_NU_GENERIC && VALUE) ?
   } else if (t < 2 * TILE) {
     const long long c = (c0 + (t - TILE) < n2) ? c0 + (t - TILE) : n2 - 1;
     pc[t - TILE] = PT::prepare(xy2[2 * c], xy2[2 * c + 1]);
+  }
+  constexpr bool TAB = (MODE == CK_NU_GENERIC && VALUE != 0);
+  __shared__ double stab[TAB ? CK_TAB_NC * CK_TAB_NSEG : 1];  // generic nu: the block's correlation table (8.4 KB)
+  if constexpr (TAB) {
+    const double* src = &tab.T.c[0][0];
+    for (int i = t; i < CK_TAB_NC * CK_TAB_NSEG; i += K1_THREADS) stab[i] = src[i];
   }
   __syncthreads();
   const int tx = t & 31, ty = t >> 5;  // 8 warps; warp `ty` owns rows ty, ty+8, ...
@@ -233,8 +248,11 @@ __global__ void __launch_bounds__(K1_THREADS, (MODE == CK_NU_GENERIC && VALUE) ?
       for (int c = 0; c < 2; ++c) {
         const int lc = tx + 32 * c;
         const double h = PT::dist(pr[lr], pc[lc]);
-        const double val = VALUE ? ck_matern_cov<MODE>(P, h)  // generic order: K_nu by series / Chebyshev fits
-                                 : h;                         // distance output: reference operation order
+        double val = h;  // distance output: reference operation order
+        if constexpr (TAB) {  // generic order: piecewise Chebyshev table of rho(x) e^x (ck_math.cuh)
+          val = P.scale * ck_matern_corr_tab(P, stab, h);
+          if (h == 0.0) val += P.nugget;
+        }
         if (r0 + lr < n1 && c0 + lc < n2) out[(r0 + lr) * ld + (c0 + lc)] = val;
         if (mirror) tr[lr][lc] = val;
       }
@@ -257,14 +275,22 @@ __global__ void __launch_bounds__(K1_THREADS, (MODE == CK_NU_GENERIC && VALUE) ?
 template <int METRIC, int VALUE>
 static void launch_mode(const CkMatern& P, dim3 grid, cudaStream_t st, const double* xy1, long long n1, const double* xy2,
                         long long n2, double* out, long long ld, double* out_t, long long ld_t, int symmetric) {
-#define CK_K1(MODE) ck_block_kernel<METRIC, MODE, VALUE><<<grid, K1_THREADS, 0, st>>>(xy1, n1, xy2, n2, P, out, ld, out_t, ld_t, symmetric)
+#define CK_K1(MODE) \
+  ck_block_kernel<METRIC, MODE, VALUE><<<grid, K1_THREADS, 0, st>>>(xy1, n1, xy2, n2, P, out, ld, out_t, ld_t, symmetric, K1TabArg<false>())
   if (!VALUE) { CK_K1(CK_NU_HALF); return; }
   switch (P.mode) {
     case CK_NU_HALF: CK_K1(CK_NU_HALF); break;
     case CK_NU_3HALF: CK_K1(CK_NU_3HALF); break;
     case CK_NU_5HALF: CK_K1(CK_NU_5HALF); break;
     case CK_NU_7HALF: CK_K1(CK_NU_7HALF); break;
-    default: CK_K1(CK_NU_GENERIC); break;
+    default: {
+      if constexpr (VALUE != 0) {
+        static thread_local K1TabArg<true> targ;  // 8.4 KB, copied into the launch's parameter buffer by the <<<>>> call
+        ck_matern_table_setup(P, &targ.T);
+        ck_block_kernel<METRIC, CK_NU_GENERIC, VALUE><<<grid, K1_THREADS, 0, st>>>(xy1, n1, xy2, n2, P, out, ld, out_t, ld_t,
+                                                                                 symmetric, targ);
+      }
+    } break;
   }
 #undef CK_K1
 }

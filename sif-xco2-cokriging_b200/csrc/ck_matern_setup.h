@@ -77,7 +77,7 @@ static inline int ck_matern_setup(CkMatern* P, double scale, double nu, double l
   else if (nu == 2.5) P->mode = CK_NU_5HALF;
   else if (nu == 3.5) P->mode = CK_NU_7HALF;
   else P->mode = CK_NU_GENERIC;
-  P->x_cut = 1.0e308;
+  P->x_cut = 1.0e308;  // generic nu: set after the K_nu constants below (the predicate needs them)
   if (P->mode != CK_NU_GENERIC) {  // smallest double x at which the reference-order underflow predicate fires
     double lo = 600.0, hi = 760.0;  // predicate false at lo, true at hi
     for (int it = 0; it < 200 && nextafter(lo, hi) < hi; ++it) {
@@ -157,5 +157,64 @@ static inline int ck_matern_setup(CkMatern* P, double scale, double nu, double l
   }
   const long double pm = 3.14159265358979323846264338327950288L * mu;
   P->mu_pi_ratio = (fabsl(pm) < 1.0e-9L) ? 1.0 : (double)(pm / sinl(pm));
+  if (P->mode == CK_NU_GENERIC) {  // smallest double x with K_nu(x) below the AMOS cut-off (K_nu is decreasing in x)
+    double lo = 600.0, hi = 800.0;
+    for (int it = 0; it < 200 && nextafter(lo, hi) < hi; ++it) {
+      const double mid = lo + 0.5 * (hi - lo);
+      if (ck_besselk(*P, mid) < CK_KV_UNDERFLOW) hi = mid; else lo = mid;
+    }
+    P->x_cut = hi;
+  }
+  return 0;
+}
+
+// Piecewise Chebyshev table of g(x) = rho(x) e^x for a generic-nu block (see ck_math.cuh).  Node values: x >= 2 from the
+// long-double continued fraction (sqrt(x) e^x K_mu, K_mu+1 without any exponential) and the forward recurrence in long
+// double; x < 2 from the double-precision Temme series.  Cached by nu (a bivariate model has three blocks, re-created for
+// every call of one parameter vector).  Returns 0, or -1 if P is not a generic-nu block.
+static inline int ck_matern_table_setup(const CkMatern& P, CkMaternTable* T) {
+  if (P.mode != CK_NU_GENERIC) return -1;
+  struct TabCache { double nu; int valid; CkMaternTable tab; };
+  static thread_local TabCache cache[6];
+  static thread_local int next_slot = 0;
+  for (int i = 0; i < 6; ++i)
+    if (cache[i].valid && cache[i].nu == P.nu) { memcpy(T, &cache[i].tab, sizeof(*T)); return 0; }
+  const long double pi = 3.14159265358979323846264338327950288L;
+  const long double nu = (long double)P.nu, mu = (long double)P.mu;
+  const long double lc = (1.0L - nu) * logl(2.0L) - lgammal(nu);
+  auto g_of = [&](long double x) -> long double {
+    if (x >= 2.0L) {
+      long double k0, k1;  // sqrt(x) e^x K_mu, K_(mu+1)
+      ck_knu_cf2_nodes(mu, x, &k0, &k1);
+      for (int i = 1; i <= P.nl; ++i) {
+        const long double t = (mu + (long double)i) * (2.0L / x) * k1 + k0;
+        k0 = k1;
+        k1 = t;
+      }
+      return expl(lc + (nu - 0.5L) * logl(x)) * k0;  // c x^nu K_nu e^x = c x^(nu - 1/2) [sqrt(x) e^x K_nu]
+    }
+    const double xd = (double)x;
+    return expl(lc + nu * logl(x) + x) * (long double)ck_besselk(P, xd);
+  };
+  TabCache* slot = &cache[next_slot];
+  next_slot = (next_slot + 1) % 6;
+  slot->valid = 0;
+  long double cosjk[CK_TAB_NC][CK_TAB_NC];
+  for (int j = 0; j < CK_TAB_NC; ++j)
+    for (int k = 0; k < CK_TAB_NC; ++k) cosjk[j][k] = cosl(pi * (long double)j * ((long double)k + 0.5L) / CK_TAB_NC);
+  for (int sg = 0; sg < CK_TAB_NSEG; ++sg) {
+    const int e = CK_TAB_EMIN + sg / 4, q = sg % 4;
+    const long double a = ldexpl(1.0L + 0.25L * q, e), b = ldexpl(1.0L + 0.25L * (q + 1), e);
+    long double y[CK_TAB_NC];
+    for (int k = 0; k < CK_TAB_NC; ++k) y[k] = g_of(0.5L * (a + b) + 0.5L * (b - a) * cosjk[1][k]);
+    for (int j = 0; j < CK_TAB_NC; ++j) {
+      long double acc = 0.0L;
+      for (int k = 0; k < CK_TAB_NC; ++k) acc += y[k] * cosjk[j][k];
+      slot->tab.c[j][sg] = (double)((j == 0 ? 1.0L : 2.0L) * acc / CK_TAB_NC);
+    }
+  }
+  slot->nu = P.nu;
+  slot->valid = 1;
+  memcpy(T, &slot->tab, sizeof(*T));
   return 0;
 }

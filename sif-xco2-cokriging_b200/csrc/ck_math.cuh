@@ -14,6 +14,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define CK_HD __host__ __device__ __forceinline__
@@ -298,6 +299,42 @@ CK_HD double ck_matern_cov_dyn(const CkMatern& P, double h) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Generic nu in the ASSEMBLY kernel: piecewise Chebyshev table of g(x) = rho(x) e^x, rho(x) = 2^(1-nu)/Gamma(nu) x^nu K_nu(x).
+// K_nu costs ~500 FP64 instructions per entry (series / fits of two orders + recurrence + log + two exp), data dependent
+// and divergent between the x <= 2 and x > 2 lanes of a warp.  g is analytic and slowly varying for x > 0, so on quarter-
+// octave segments [2^e (1 + q/4), 2^e (1 + (q+1)/4)) a degree-11 Chebyshev fit is accurate to ~1e-14 (Bernstein-ellipse
+// parameter ~20); the segment index is the biased exponent and the top two mantissa bits of x -- integer work only -- and
+// the local variable u in [-1, 1) comes from the remaining mantissa bits with one FMA.  Per entry: 12 shared-memory loads,
+// a 12-term Clenshaw recurrence and one exp(-x): ~70 instructions.  The table (one per model block, 8.4 KB) is fitted on
+// the host (ck_matern_setup.h) from the long-double continued fraction (x >= 2) / the Temme series (x < 2).
+// x below 2^CK_TAB_EMIN (h of a few metres at l = 500 km) takes the series path; x >= x_cut is the kv underflow flush.
+// ------------------------------------------------------------------------------------------------
+#define CK_TAB_EMIN (-12)
+#define CK_TAB_EMAX 10
+#define CK_TAB_NSEG (4 * (CK_TAB_EMAX - CK_TAB_EMIN))
+#define CK_TAB_NC 12
+struct CkMaternTable {
+  double c[CK_TAB_NC][CK_TAB_NSEG];  // coefficient-major: lanes in different segments read different banks
+};
+
+// segment index of x > 0 (may be < 0 or >= CK_TAB_NSEG) and the local variable u in [-1, 1)
+CK_HD int ck_tab_locate(double x, double* u) {
+  long long bits;
+  memcpy(&bits, &x, sizeof(bits));
+  const int hi = (int)(bits >> 32);
+  const int idx = (hi >> 18) - ((1023 + CK_TAB_EMIN) << 2);  // 4 * (exponent - EMIN) + top two mantissa bits
+  const int q = (hi >> 18) & 3;
+  const long long ybits = (bits & 0x000FFFFFFFFFFFFFLL) | 0x3FF0000000000000LL;  // mantissa with exponent 0: y in [1, 2)
+  double y;
+  memcpy(&y, &ybits, sizeof(y));
+  *u = fma(8.0, y, -9.0 - 2.0 * (double)q);  // f = 4 (y - 1) - q in [0, 1), u = 2 f - 1
+  return idx;
+}
+
+// Matern correlation from the table (tab = &T.c[0][0], stride CK_TAB_NSEG between coefficients)
+CK_HD double ck_matern_corr_tab(const CkMatern& P, const double* tab, double h);  // defined after ck_fast_exp_neg
+
+// ------------------------------------------------------------------------------------------------
 // Fast, branch-free variants for the covariance-ASSEMBLY kernel (K1, half-integer nu).  The reference-order
 // functions above reproduce the reference's operation order (bit-identical Euclidean distances, libm-level
 // haversine) and are what the distance output, the variogram binning and the local-neighbourhood kernels use.
@@ -400,6 +437,27 @@ CK_HD double ck_fast_exp_neg(double x) {
 #else
   return ldexp(p, (int)nf);
 #endif
+}
+
+CK_HD double ck_matern_corr_tab(const CkMatern& P, const double* tab, double h) {
+  h = fabs(h);
+  if (!(h > 0.0)) return 1.0;  // h == 0 and NaN (the reference's `h > 0` mask is False): rho = 1
+  const double x = CK_MUL(P.sqrt2nu, CK_DIV(h, P.len_scale));  // reference order: (h / l) then * sqrt(2 nu)
+  if (!(x < P.x_cut)) return 0.0;                              // kv underflow flush (and +inf)
+  double u;
+  const int idx = ck_tab_locate(x, &u);
+  if (idx < 0 || idx >= CK_TAB_NSEG) return ck_matern_corr<CK_NU_GENERIC>(P, h);  // x < 2^EMIN: series
+  const double u2 = 2.0 * u;
+  double b1 = 0.0, b2 = 0.0;
+#pragma unroll
+  for (int j = CK_TAB_NC - 1; j >= 1; --j) {
+    const double nb = CK_FMA(u2, b1, tab[j * CK_TAB_NSEG + idx] - b2);
+    b2 = b1;
+    b1 = nb;
+  }
+  const double g = CK_FMA(u, b1, tab[idx] - b2);
+  const double rho = g * ck_fast_exp_neg(x);
+  return rho > 0.0 ? rho : 0.0;
 }
 
 CK_HD double ck_dist_euclid_fast(const CkPoint& p, const CkPoint& q) {

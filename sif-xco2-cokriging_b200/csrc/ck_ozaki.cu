@@ -79,10 +79,27 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s
   }
 }
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar), "l"(policy)
                : "memory");
+}
+// L2 eviction priorities (OzGemmArgs::l2_hints): the operand slices are re-read by every tile of a super-row while the C
+// tiles stream through exactly once (one read, one write), so the slices are loaded evict_last and C evict_first
+__device__ __forceinline__ uint64_t l2_policy(int kind) {  // 0 normal, 1 evict_last, 2 evict_first
+  uint64_t p;
+  if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  else if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ double2 ld_c2(const double* p, uint64_t policy) {
+  double2 v;
+  asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(policy) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_c2(double* p, double2 v, uint64_t policy) {
+  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(policy) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -235,6 +252,7 @@ struct OzGemmArgs {
   int tb;
   long long gi0, gis, gj0, gjs;
   int vec;            // C is 16-byte aligned with an even leading dimension
+  int l2_hints;       // bit 0: operand slices evict_last, bit 1: C loads / stores evict_first (CK_OZ_L2_HINTS)
   long long* dbg;     // optional per-CTA cycle counters (8 per CTA), see ck_oz_debug_buffer
 };
 
@@ -315,6 +333,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ck_oz_gemm_kernel(OzGemmArgs g)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      const uint64_t pol = l2_policy((g.l2_hints & 1) ? 1 : 0);
       for (long long t = blockIdx.x; t < g.nvirt; t += gridDim.x) {
         int I, j;
         if (!oz_decode(g, t, I, j)) continue;
@@ -324,8 +343,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ck_oz_gemm_kernel(OzGemmArgs g)
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_expect_tx(full_bar(stage), OZ_STAGE);
           const uint32_t dst = smem0 + (uint32_t)stage * OZ_STAGE;
-          bulk_g2s(dst, ga + (size_t)kc * OZ_A_STAGE, OZ_A_STAGE, full_bar(stage));
-          bulk_g2s(dst + OZ_A_STAGE, gb + (size_t)kc * OZ_B_STAGE, OZ_B_STAGE, full_bar(stage));
+          bulk_g2s(dst, ga + (size_t)kc * OZ_A_STAGE, OZ_A_STAGE, full_bar(stage), pol);
+          bulk_g2s(dst + OZ_A_STAGE, gb + (size_t)kc * OZ_B_STAGE, OZ_B_STAGE, full_bar(stage), pol);
           if (++stage == OZ_NSTAGE) { stage = 0; phase ^= 1u; }
         }
       }
@@ -391,6 +410,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ck_oz_gemm_kernel(OzGemmArgs g)
     constexpr int EC = OZ_TN / (OZ_EPI_WARPS / 4);  // columns per thread
     const int qd = warp & 3, half = (warp - 2) >> 2;
     uint32_t aphase = 0;
+    const uint64_t cpol = l2_policy((g.l2_hints & 2) ? 2 : 0);
     long long t_busy = 0, t_wait = 0;
     for (long long t = blockIdx.x; t < g.nvirt; t += gridDim.x) {
       int I, j;
@@ -407,7 +427,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ck_oz_gemm_kernel(OzGemmArgs g)
       if (fast) {
 #pragma unroll
         for (int i = 0; i < EC; i += 2) {
-          const double2 cv = *reinterpret_cast<const double2*>(crow + i);
+          const double2 cv = ld_c2(crow + i, cpol);
           creg[i] = cv.x;
           creg[i + 1] = cv.y;
         }
@@ -447,7 +467,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ck_oz_gemm_kernel(OzGemmArgs g)
       aphase ^= 1u;
       if (fast) {
 #pragma unroll
-        for (int i = 0; i < EC; i += 2) *reinterpret_cast<double2*>(crow + i) = make_double2(creg[i], creg[i + 1]);
+        for (int i = 0; i < EC; i += 2) st_c2(crow + i, make_double2(creg[i], creg[i + 1]), cpol);
       } else if (row_ok) {
 #pragma unroll
         for (int i = 0; i < EC; ++i)
@@ -550,6 +570,12 @@ static int oz_gemm_launch(const void* a_slices, const double* sa, ck_i64 m, cons
   g.tri = (g.lower && (long long)g.nj >= 2LL * g.ni - 1) ? 1 : 0;
   g.nvirt = g.tri ? (long long)g.sr * g.sr * srows * (srows + 1) : srows * (long long)g.sr * g.nj;
   g.vec = ((((uintptr_t)c) & 15) == 0 && (ldc & 1) == 0) ? 1 : 0;
+  static int hints_cfg = -1;
+  if (hints_cfg < 0) {
+    const char* e = getenv("CK_OZ_L2_HINTS");
+    hints_cfg = e ? (atoi(e) & 3) : 0;
+  }
+  g.l2_hints = hints_cfg;
   g.dbg = g_oz_dbg;
   long long grid = oz_num_sms();
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;  // caller leaves SMs to a concurrent stream (look-ahead)

@@ -101,6 +101,15 @@ def hostmath():
                              out.ctypes.data_as(dp))
         return out
 
+    def _matern_table(scale, nu, ell, nugget, h):
+        h = np.ascontiguousarray(h, float)
+        out = np.empty_like(h)
+        rc = lib.ckh_matern_cov_table(ctypes.c_double(scale), ctypes.c_double(nu), ctypes.c_double(ell), ctypes.c_double(nugget),
+                                      h.ctypes.data_as(dp), ctypes.c_long(h.size), out.ctypes.data_as(dp))
+        assert rc == 0, rc
+        return out
+
+    H.matern_cov_table = staticmethod(_matern_table)
     H.distance_pre = staticmethod(_dist_pre)
     H.distance_fast = staticmethod(_dist_fast)
     H.matern_cov_fast = staticmethod(_matern_fast)

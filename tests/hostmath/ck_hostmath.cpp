@@ -22,6 +22,20 @@ int ckh_matern_cov(double scale, double nu, double len_scale, double nugget, con
   return 0;
 }
 
+// generic nu through the piecewise Chebyshev table of the assembly kernel (ck_matern_corr_tab)
+int ckh_matern_cov_table(double scale, double nu, double len_scale, double nugget, const double* h, long n, double* out) {
+  CkMatern P;
+  if (ck_matern_setup(&P, scale, nu, len_scale, nugget)) return -1;
+  static CkMaternTable T;
+  if (ck_matern_table_setup(P, &T)) return -2;
+  for (long i = 0; i < n; ++i) {
+    double c = P.scale * ck_matern_corr_tab(P, &T.c[0][0], h[i]);
+    if (h[i] == 0.0) c += P.nugget;
+    out[i] = c;
+  }
+  return 0;
+}
+
 int ckh_distance(int metric, const double* X1, long n1, const double* X2, long n2, double* out) {
   for (long i = 0; i < n1; ++i) {
     const CkPoint p = ck_prepare_point(metric, X1[2 * i], X1[2 * i + 1]);

@@ -172,3 +172,39 @@ def test_besselk_chebyshev_branch_vs_mpmath(hostmath):
     for nu in (0.05, 0.2, 0.39, 0.75, 0.82, 1.0, 1.25, 1.49, 2.0, 2.3, 3.0, 3.2, 7.7):
         truth = np.array([float(mp.besselk(nu, mp.mpf(float(v)))) for v in x])
         assert relerr(hostmath.besselk(nu, x), truth) < 2e-15, nu
+
+
+def test_generic_nu_table_vs_reference_fixture_and_mpmath(hostmath):
+    """K1's generic-nu path: piecewise Chebyshev table of rho(x) e^x on quarter-octave segments (ck_matern_corr_tab,
+    fitted per block by ck_matern_table_setup) -- reference fixture (scipy kv through the unmodified reference), the
+    far-field flush to exactly 0, special values, segment edges, and mpmath truth."""
+    g = golden("matern")
+    for a, nu in enumerate(g["nus"]):
+        if nu in (0.5, 1.5, 2.5, 3.5):
+            continue
+        for b, ell in enumerate(g["lens"]):
+            got = hostmath.matern_cov_table(1.0, nu, ell, 0.0, g["h"])
+            ref = g["corr"][a, b]
+            nz = ref > 0
+            assert relerr(got[nz], ref[nz]) < TOL_COV, (nu, ell)
+            assert ((ref == 0) == (got == 0)).all()
+    got, ref = hostmath.matern_cov_table(1.0, 0.82, 0.002, 0.0, g["far_h"]), g["far_corr"][1]
+    assert ((ref == 0) == (got == 0)).all()
+    assert relerr(got[ref > 0], ref[ref > 0]) < TOL_COV
+    h = np.array([0.0, -3.0, np.nan, np.inf])
+    got = hostmath.matern_cov_table(2.0, 0.82, 10.0, 0.25, h)
+    assert got[0] == 2.25 and got[2] == 2.0 and got[3] == 0.0
+    assert got[1] == pytest.approx(hostmath.matern_cov(2.0, 0.82, 10.0, 0.25, h)[1], rel=1e-13)
+    mp = pytest.importorskip("mpmath")
+    mp.mp.dps = 40
+    rng = np.random.default_rng(11)
+    edges = np.array([2.0 ** e * (1 + q / 4) for e in range(-12, 10) for q in range(4)])
+    x = np.concatenate([10 ** rng.uniform(-6, 2.8, 400), edges, np.nextafter(edges, 0), np.nextafter(edges, np.inf),
+                        [2.0 ** -13, 1.0e-5, 680.0]])
+    for nu in (0.05, 0.2, 0.39, 0.82, 1.0, 1.25, 2.0, 2.3, 3.2, 7.7):
+        sq = np.sqrt(2 * nu)
+        truth = np.array([float(2 ** (1 - mp.mpf(nu)) / mp.gamma(nu) * mp.mpf(float(v)) ** nu * mp.besselk(nu, mp.mpf(float(v))))
+                          for v in x])
+        got = hostmath.matern_cov_table(1.0, nu, 1.0, 0.0, x / sq)  # x = sqrt(2 nu) h / l up to one rounding of h
+        ok = truth > 1e-290
+        assert relerr(got[ok], truth[ok]) < 1e-13, nu
