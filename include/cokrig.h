@@ -290,6 +290,63 @@ int ck_row_dots(const double* v_dev, ck_i64 ldv, ck_i64 nrows, ck_i64 ncols, con
                 double* out_vy_dev, double* out_vv_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Multi-GPU handle API: the whole block-cyclic sweep driven from C (ck_mg_create /
+ * ck_mg_joint_cov / ck_mg_potrf / ck_mg_potrs_predict / ck_mg_destroy).  One process (or host
+ * thread) per GPU; every rank makes the same sequence of calls with the same arguments (replicated
+ * coordinates and data).  The context owns a world, a process-row and a process-column NCCL
+ * communicator (bound at run time: dlopen of libnccl.so.2, env CK_NCCL_LIB overrides; world = 1
+ * never touches NCCL) and a high-priority panel stream for the one-panel look-ahead.  Together the
+ * three calls replace, for one system spread over P x Q GPUs, what the reference does in one
+ * process: _joint_cov / _pred_cross_cov (src/joint_prediction.py:94-153), cho_factor, cho_solve and
+ * the prediction / variance products (src/joint_prediction.py:68-78).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct ck_mg_ctx ck_mg_ctx;
+
+/* 128-byte NCCL unique id (HOST buffer): call on ONE rank and hand the bytes to every rank's
+ * ck_mg_create through whatever channel the host program has (MPI, a socket, a file). */
+int ck_mg_unique_id(void* id128 /*HOST*/);
+
+/* Collective over all `world` ranks: rank = p * Q + q on a P x Q process grid, square tiles of `tile`
+ * elements (multiple of 128, at most 1024).  The current CUDA device of the calling thread becomes the
+ * context's device.  nccl_unique_id128 may be NULL when world == 1.  Env knobs read here:
+ * CK_MG_LOOKAHEAD (default 1), CK_MG_PANEL_SMS (default: adaptive per tile column), CK_MG_INT8_MIN_TILES. */
+int ck_mg_create(ck_mg_ctx** out /*HOST*/, int world, int rank, int P, int Q, ck_i64 tile, const void* nccl_unique_id128 /*HOST*/);
+int ck_mg_destroy(ck_mg_ctx* h);
+int ck_mg_grid(const ck_mg_ctx* h, int* pq4 /*HOST: P, Q, p, q*/);
+
+/* Device bytes this rank needs for a system of n_data stacked data and m targets: its tiles of the
+ * augmented array, the double-buffered panel operands, exchange buffers and the int8 slice scratch. */
+size_t ck_mg_workspace_bytes(ck_mg_ctx* h, ck_i64 n_data, ck_i64 m);
+
+/* Assemble this rank's tiles of [Sigma ; C^T + z] (ck_mg_assemble) inside ws_dev, which must stay
+ * alive until the predictions have been read.  Arguments as ck_joint_cov + ck_cross_cov. */
+int ck_mg_joint_cov(ck_mg_ctx* h, const double* xy0_dev, ck_i64 n0, const double* xy1_dev, ck_i64 n1, const double* xyp_dev,
+                    ck_i64 m, const double* z_dev, const double* params /*HOST*/, int n_procs, int i_pred, int metric,
+                    void* ws_dev, size_t ws_bytes, void* stream);
+
+/* The sweep: right-looking tile Cholesky over all rows of the augmented array with NCCL panel broadcasts
+ * (diagonal tile down the process column, panel rows along each process row, panel columns inside each
+ * process column) and one-panel look-ahead on the context's panel stream; trailing updates on `stream`.
+ * Leaves L in the data tiles, L^-1 c and L^-1 z in the target tiles. */
+int ck_mg_potrf(ck_mg_ctx* h, void* stream);
+
+/* pred[c] = (L^-1 c).(L^-1 z), var[c] = c0 - |L^-1 c|^2 for all m targets on EVERY rank (per-rank row
+ * partial sums all-gathered and added in rank order: deterministic); *info_dev (device int) = 0 or the
+ * order of the first non-positive-definite leading minor, as ck_potrf. */
+int ck_mg_potrs_predict(ck_mg_ctx* h, double* pred_dev, double* var_dev, int* info_dev, void* stream);
+
+/* logdet(Sigma) = 2 sum log L_kk over the diagonal tiles of all ranks -> *out_dev on every rank. */
+int ck_mg_logdet(ck_mg_ctx* h, double* out_dev, void* stream);
+
+/* Milliseconds of the last assemble / sweep / predict phases on this rank (synchronises on their events). */
+int ck_mg_times_ms(ck_mg_ctx* h, double* out3 /*HOST*/);
+
+/* This rank's part of the array (diagnostics: sampled checks of L L^T): local tile (li, lj) = global
+ * tile (li P + p, lj Q + q) at local_dev + li*tile*ld + lj*tile. */
+int ck_mg_local_factor(ck_mg_ctx* h, double** local_dev /*HOST*/, ck_i64* ld /*HOST*/, ck_i64* local_row_tiles /*HOST*/,
+                       ck_i64* local_col_tiles /*HOST*/);
+
+/* ------------------------------------------------------------------------------------------------
  * K3 (INT8 tensor-core path)  FP64-equivalent rank-k updates  C -= A B^T  by fixed-slice error-free
  * splitting (7 balanced base-256 digits per operand, 28 int8 x int8 -> int32 slice products in TMEM,
  * FP64 recombination in the epilogue).  ck_potrf / ck_trsm_lower use these internally for their big

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "cokrig_b200", "libcokrig_b200.so")
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["ck_matern.cu", "ck_chol.cu", "ck_vario.cu", "ck_local.cu", "ck_mg.cu", "ck_ozaki.cu", "ck_xcor.cu"]
+SOURCES = ["ck_matern.cu", "ck_chol.cu", "ck_vario.cu", "ck_local.cu", "ck_mg.cu", "ck_mgctx.cu", "ck_ozaki.cu", "ck_xcor.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

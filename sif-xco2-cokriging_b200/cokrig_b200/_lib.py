@@ -73,6 +73,18 @@ SIGNATURES = {
     "ck_mg_local_tiles": (c_int64, [c_int64, c_int64, c_int64]),
     "ck_mg_assemble": (c_int, [_dp, c_int64, _dp, c_int64, _dp, c_int64, _dp, _hp, c_int, c_int, c_int, c_int64,
                                c_int, c_int, c_int, c_int, _dp, c_int64, c_void_p]),
+    "ck_mg_unique_id": (c_int, [c_void_p]),
+    "ck_mg_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int64, c_void_p]),
+    "ck_mg_destroy": (c_int, [c_void_p]),
+    "ck_mg_grid": (c_int, [c_void_p, POINTER(c_int)]),
+    "ck_mg_workspace_bytes": (c_size_t, [c_void_p, c_int64, c_int64]),
+    "ck_mg_joint_cov": (c_int, [c_void_p, _dp, c_int64, _dp, c_int64, _dp, c_int64, _dp, _hp, c_int, c_int, c_int, _dp, c_size_t,
+                                c_void_p]),
+    "ck_mg_potrf": (c_int, [c_void_p, c_void_p]),
+    "ck_mg_potrs_predict": (c_int, [c_void_p, _dp, _dp, _dp, c_void_p]),
+    "ck_mg_logdet": (c_int, [c_void_p, _dp, c_void_p]),
+    "ck_mg_times_ms": (c_int, [c_void_p, _hp]),
+    "ck_mg_local_factor": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)]),
     "ck_gemm_nt": (c_int, [_dp, c_int64, _dp, c_int64, _dp, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p]),
     "ck_mg_update": (c_int, [_dp, c_int64, _dp, c_int64, _dp, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
                              c_int64, c_int64, c_int64, c_void_p]),

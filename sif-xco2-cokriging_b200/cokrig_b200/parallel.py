@@ -20,6 +20,7 @@ partitioning, communication order and reductions without a GPU.
 """
 from __future__ import annotations
 
+import ctypes
 import os
 from typing import Callable, List, Optional, Sequence, Tuple
 
@@ -669,3 +670,90 @@ class BlockCyclicCokriging:
             else:
                 out[name + "_ms"] = ev[a].elapsed_time(ev[b])
         return out
+
+
+# ------------------------------------------------------------------------------------------------ native handle API
+class NativeBlockCyclic:
+    """The same sweep through the C handle API of libcokrig_b200.so (csrc/ck_mgctx.cu: ck_mg_create / ck_mg_joint_cov /
+    ck_mg_potrf / ck_mg_potrs_predict / ck_mg_destroy) -- schedule, streams, events and the NCCL row / column
+    communicators all live behind the C ABI; this class only allocates the workspace and moves the 128-byte NCCL id
+    between the ranks (torch.distributed, any backend).  It is what a C / C++ host program would call directly
+    (INTEGRATION.md); `BlockCyclicCokriging` is the torch.distributed twin whose orchestration the gloo CPU tests cover."""
+
+    def __init__(self, P: Optional[int] = None, Q: Optional[int] = None, tile: int = 1024, device=None):
+        from . import ops
+        from ._lib import check, lib
+        self.ops, self.lib, self.check = ops, lib, check
+        self.device = ops.require_cuda() if device is None else torch.device(device)
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        if P is None or Q is None:
+            P, Q = grid_shape(self.world)
+        uid = (ctypes.c_ubyte * 128)()
+        if self.world > 1:
+            if self.rank == 0:
+                check(lib.ck_mg_unique_id(uid), "ck_mg_unique_id")
+            box = [bytes(uid)]
+            dist.broadcast_object_list(box, src=0)
+            uid = (ctypes.c_ubyte * 128).from_buffer_copy(box[0])
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib.ck_mg_create(ctypes.byref(self._h), self.world, self.rank, int(P), int(Q), int(tile), uid), "ck_mg_create")
+        self.P, self.Q, self.tile = int(P), int(Q), int(tile)
+        self._ws = None
+        self.timings = {}
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            torch.cuda.synchronize(self.device)
+            self.lib.ck_mg_destroy(self._h)
+            self._h.value = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001  (interpreter shutdown)
+            pass
+
+    def local_bytes(self, N: int, m: int) -> int:
+        return int(self.lib.ck_mg_workspace_bytes(self._h, int(N), int(m)))
+
+    def solve_device(self, coords_d: Sequence, z_d, t_d, params, n_procs: int, i_pred: int, metric: int):
+        """Device-resident replicated inputs -> (pred, var, info) device tensors, nothing synchronised."""
+        o, lib = self.ops, self.lib
+        _, pp = o._params(params, n_procs)
+        N, m = int(z_d.shape[0]), int(t_d.shape[0])
+        need = self.local_bytes(N, m)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        c1 = coords_d[1] if n_procs == 2 else None
+        n1 = int(coords_d[1].shape[0]) if n_procs == 2 else 0
+        pred = torch.empty(max(m, 1), dtype=F64, device=self.device)
+        var = torch.empty(max(m, 1), dtype=F64, device=self.device)
+        info = torch.zeros(1, dtype=torch.int32, device=self.device)
+        st = o._stream()
+        self.check(lib.ck_mg_joint_cov(self._h, o._ptr(coords_d[0]), int(coords_d[0].shape[0]), o._ptr(c1), n1, o._ptr(t_d), m,
+                                       o._ptr(z_d), pp, n_procs, i_pred, metric, o._ptr(self._ws), self._ws.numel(), st),
+                   "ck_mg_joint_cov")
+        self.check(lib.ck_mg_potrf(self._h, st), "ck_mg_potrf")
+        self.check(lib.ck_mg_potrs_predict(self._h, o._ptr(pred), o._ptr(var), o._ptr(info), st), "ck_mg_potrs_predict")
+        return pred[:m], var[:m], info
+
+    def solve(self, coords: Sequence, z, targets, params, n_procs: int, i_pred: int, metric: int):
+        """Host arrays replicated on every rank -> (pred, var, info) as numpy arrays / int, identical on every rank."""
+        o = self.ops
+        coords_d = [o.to_device(np.ascontiguousarray(np.asarray(c, dtype=np.float64))) for c in coords[:n_procs]]
+        z_d = o.to_device(np.ascontiguousarray(np.hstack([np.asarray(v, dtype=np.float64) for v in z[:n_procs]])))
+        t_d = o.to_device(np.ascontiguousarray(np.asarray(targets, dtype=np.float64)))
+        pred, var, info = self.solve_device(coords_d, z_d, t_d, params, n_procs, i_pred, metric)
+        out = pred.cpu().numpy(), var.cpu().numpy(), int(info.item())
+        t = (ctypes.c_double * 3)()
+        self.check(self.lib.ck_mg_times_ms(self._h, t), "ck_mg_times_ms")
+        self.timings = {"assemble_ms": t[0], "factor_solve_ms": t[1], "reduce_ms": t[2]}
+        return out
+
+    def logdet(self) -> float:
+        out = torch.zeros(1, dtype=F64, device=self.device)
+        self.check(self.lib.ck_mg_logdet(self._h, self.ops._ptr(out), self.ops._stream()), "ck_mg_logdet")
+        return float(out.item())

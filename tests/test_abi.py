@@ -123,3 +123,22 @@ def test_library_contains_blackwell_native_sass():
     for mnemonic in ("UTCIMMA", "LDTM", "UBLKCP", "UTCBAR"):
         assert mnemonic in oz, mnemonic
     assert "DMMA" in body("ck_potf2_inv_kernel") and "DMMA" in body("ck_gemm_nt_kernel")
+
+
+def test_multi_gpu_handle_api_argument_checks_without_a_device():
+    """ck_mg_create validates the grid before it touches CUDA or NCCL; without a device a valid request reports
+    CK_ERR_CUDA (no CPU fallback); the size query of a null context is 0."""
+    import torch
+    from cokrig_b200 import _lib
+    lib = _lib.lib
+    h = ctypes.c_void_p()
+    assert lib.ck_mg_create(ctypes.byref(h), 2, 0, 1, 1, 1024, None) == _lib.CK_ERR_ARG and "grid" in _lib.last_error()
+    assert lib.ck_mg_create(ctypes.byref(h), 1, 0, 1, 1, 100, None) == _lib.CK_ERR_ARG and "tile" in _lib.last_error()
+    assert lib.ck_mg_create(ctypes.byref(h), 4, 4, 2, 2, 1024, None) == _lib.CK_ERR_ARG
+    assert lib.ck_mg_create(ctypes.byref(h), 2, 1, 1, 2, 1024, None) == _lib.CK_ERR_ARG and "unique id" in _lib.last_error()
+    assert not h.value
+    if not torch.cuda.is_available():
+        assert lib.ck_mg_create(ctypes.byref(h), 1, 0, 1, 1, 1024, None) == _lib.CK_ERR_CUDA
+    assert lib.ck_mg_workspace_bytes(None, 10, 10) == 0
+    assert lib.ck_mg_destroy(None) == _lib.CK_OK
+    assert lib.ck_mg_potrf(None, None) == _lib.CK_ERR_ARG

@@ -75,6 +75,60 @@ def test_block_cyclic_single_rank_int8_updates_vs_oracle():
     assert np.max(np.abs(pred - pred_d)) / np.max(np.abs(rp)) < 1e-11
 
 
+@pytest.mark.parametrize("metric,params,tile", [(0, HALF, 128), (1, GENERIC_KM, 256)])
+def test_native_handle_api_single_rank_vs_oracle(metric, params, tile):
+    """csrc/ck_mgctx.cu (ck_mg_create / ck_mg_joint_cov / ck_mg_potrf / ck_mg_potrs_predict / ck_mg_logdet) on a 1 x 1 grid:
+    the C-side schedule against the oracle and against the torch.distributed twin (same kernels: same bits expected up
+    to the order of the launches, which does not change any sum)."""
+    from cokrig_b200 import parallel
+    coords, z, targets = _inputs(metric, 700, 650, 420, 17)
+    native = parallel.NativeBlockCyclic(1, 1, tile=tile)
+    twin = parallel.BlockCyclicCokriging(parallel.ProcessGrid(1, 1), tile=tile)
+    for i_pred in (0, 1):
+        pred, var, info = native.solve(coords, z, targets, params, 2, i_pred, metric)
+        rp, re, _ = orc.joint_predict(orc.Params(params), i_pred, coords, z, targets, "haversine" if metric else "euclidean")
+        assert info == 0
+        assert np.max(np.abs(pred - rp)) / np.max(np.abs(rp)) < 1e-9
+        assert np.max(np.abs(var - re ** 2)) < 1e-9
+        p2, v2, _ = twin.solve(coords, z, targets, params, 2, i_pred, metric)
+        assert np.max(np.abs(pred - p2)) <= 1e-13 * np.max(np.abs(rp)) and np.max(np.abs(var - v2)) <= 1e-13
+    sigma = orc.joint_cov(orc.Params(params), coords, "haversine" if metric else "euclidean")
+    assert abs(native.logdet() / np.linalg.slogdet(sigma)[1] - 1) < 1e-10
+    assert set(native.timings) == {"assemble_ms", "factor_solve_ms", "reduce_ms"}
+    native.close()
+
+
+def test_native_handle_api_int8_updates_and_non_pd():
+    from cokrig_b200 import parallel
+    from cokrig_b200._lib import lib
+    coords, z, targets = _inputs(0, 1500, 1400, 600, 23)
+    os.environ["CK_MG_INT8_MIN_TILES"] = "48"  # read by ck_mg_create: INT8 trailing updates, column updates and inverted-tile TRSM
+    try:
+        launches0 = lib.ck_launch_count()
+        native = parallel.NativeBlockCyclic(1, 1, tile=256)
+        pred, var, info = native.solve(coords, z, targets, HALF, 2, 1, 0)
+        n_int8 = lib.ck_launch_count() - launches0
+        twin = parallel.BlockCyclicCokriging(parallel.ProcessGrid(1, 1), tile=256, lookahead=True)
+        p2, v2, _ = twin.solve(coords, z, targets, HALF, 2, 1, 0)
+    finally:
+        del os.environ["CK_MG_INT8_MIN_TILES"]
+    launches0 = lib.ck_launch_count()
+    plain = parallel.NativeBlockCyclic(1, 1, tile=256)
+    plain.solve(coords, z, targets, HALF, 2, 1, 0)
+    assert n_int8 > lib.ck_launch_count() - launches0  # two splits + one product per big update
+    rp, re, _ = orc.joint_predict(orc.Params(HALF), 1, coords, z, targets, "euclidean")
+    assert info == 0
+    assert np.max(np.abs(pred - rp)) / np.max(np.abs(rp)) < 1e-9 and np.max(np.abs(var - re ** 2)) < 1e-9
+    assert np.max(np.abs(pred - p2)) / np.max(np.abs(rp)) < 1e-12
+    bad = [1, 1, 1.5, 1.5, 1.5, .2, .2, .2, .0, .0, -1.3]
+    c2, z2, t2 = _inputs(0, 300, 280, 20, 2)
+    _, _, info_bad = parallel.NativeBlockCyclic(1, 1, tile=128).solve(c2, z2, t2, bad, 2, 0, 0)
+    _, _, info_twin = parallel.BlockCyclicCokriging(parallel.ProcessGrid(1, 1), tile=128).solve(c2, z2, t2, bad, 2, 0, 0)
+    assert info_bad > 0 and info_bad == info_twin
+    native.close()
+    plain.close()
+
+
 def test_block_cyclic_single_rank_reports_non_pd():
     from cokrig_b200 import parallel
     coords, z, targets = _inputs(0, 300, 280, 20, 2)

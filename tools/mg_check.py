@@ -39,6 +39,7 @@ def main():
                     help="c3: bench.py's CONUS workload; c5: 1 degree global lattice, 64 800 cells per variable (co-located), "
                          "targets = random cells, nugget 0.05 (BASELINE config 5; --points is ignored)")
     ap.add_argument("--sample-rows", type=int, default=12, help="rows of L gathered for the sampled L L^T check")
+    ap.add_argument("--native", action="store_true", help="also time the C handle API (ck_mg_*) at the requested size")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
 
@@ -95,7 +96,17 @@ def main():
         report["small_pred_rel_vs_oracle"] = float(np.max(np.abs(pred - rp)) / np.max(np.abs(rp)))
         report["small_var_abs_vs_oracle"] = float(np.max(np.abs(var - re ** 2)))
         ok &= report["small_pred_rel_vs_oracle"] < 1e-9 and report["small_var_abs_vs_oracle"] < 1e-9
-    del f, solver
+    # the same system through the C handle API (csrc/ck_mgctx.cu: schedule + NCCL row / column communicators behind the ABI)
+    native = parallel.NativeBlockCyclic(P, Q, tile=256)
+    pn, vn, info_n = native.solve(coords, z, targets, PARAMS, 2, 0, METRIC_HAVERSINE)
+    report.update({"native_small_pred_rel_vs_python_sweep": float(np.max(np.abs(pn - pred)) / np.max(np.abs(p1))),
+                   "native_small_var_abs_vs_python_sweep": float(np.max(np.abs(vn - var))), "native_small_info": info_n,
+                   "native_small_pred_rel_vs_single_gpu": float(np.max(np.abs(pn - p1)) / np.max(np.abs(p1))),
+                   "native_small_logdet_abs": abs(native.logdet() - float(f.logdet().item()))})
+    ok &= (report["native_small_pred_rel_vs_single_gpu"] < 1e-9 and float(np.max(np.abs(vn - v1))) < 1e-9 and info_n == 0
+           and report["native_small_logdet_abs"] < 1e-7)
+    native.close()
+    del f, solver, native
     torch.cuda.empty_cache()
 
     # ---- 3. timed solve at the requested size
@@ -129,6 +140,32 @@ def main():
         times.append(float(t.item()))
         phases = dict(solver.timings)
     flops = N ** 3 / 3.0 + float(N) * N * (len(targets) + 1)
+    if args.native:
+        # the C handle API at the timed size: same inputs, device events around the three calls, max over ranks
+        solver_py = solver
+        native = parallel.NativeBlockCyclic(P, Q, tile=args.tile)
+        ntimes = []
+        for _ in range(args.steps + 1):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            pn, vn, info_n = native.solve(coords, z, targets, params, 2, 0, METRIC_HAVERSINE)
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ntimes.append(float(t.item()))
+        report.update({"native_solve_ms": ntimes, "native_phases_ms_rank0": dict(native.timings), "native_info": info_n,
+                       "native_pred_rel_vs_python_sweep": float(np.max(np.abs(pn - pred)) / np.max(np.abs(pred))),
+                       "native_var_abs_vs_python_sweep": float(np.max(np.abs(vn - var))),
+                       "native_local_GB": native.local_bytes(N, len(targets)) / 1e9})
+        ok &= info_n == 0 and report["native_pred_rel_vs_python_sweep"] < 1e-9 and report["native_var_abs_vs_python_sweep"] < 1e-9
+        native.close()
+        del native
+        torch.cuda.empty_cache()
     report.update({"workload": args.workload, "N": N, "m": len(targets), "tile": args.tile, "grid": f"{P}x{Q}", "solve_ms": times, "info": info,
                    "phases_ms_rank0": phases, "TFs_aggregate": flops / (min(times) / 1e3) / 1e12,
                    "predictions_per_s": len(targets) / (min(times) / 1e3)})
