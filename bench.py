@@ -520,6 +520,36 @@ def run_gpu(args, n_per_var: int, m: int) -> None:
     h2d = 8 * (2 * N + N + 2 * m) * (world if strong else 1)  # strong: inputs are replicated on every rank
     d2h = (8 * 2 * m + 4) * (world if strong else 1)
 
+    # ---- N > 1: the same sweep through the C handle API (ck_mg_create / ck_mg_joint_cov / ck_mg_potrf / ck_mg_potrs_predict:
+    # schedule + NCCL row / column communicators behind the C ABI), device-resident inputs, max over ranks
+    native = None
+    if strong and not args.no_native:
+        try:
+            ns = parallel.NativeBlockCyclic(solver.g.P, solver.g.Q, tile=args.tile)
+            for _ in range(2):
+                pn, vn, info_n = ns.solve_device(cd, zd, pd_, PARAMS, 2, I_PRED, METRIC_HAVERSINE)
+            barrier()
+            n0_, n1_ = _ev(), _ev()
+            n0_.record()
+            for _ in range(args.steps):
+                pn, vn, info_n = ns.solve_device(cd, zd, pd_, PARAMS, 2, I_PRED, METRIC_HAVERSINE)
+            n1_.record()
+            barrier()
+            tn = torch.tensor([n0_.elapsed_time(n1_) / args.steps], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tn, op=dist.ReduceOp.MAX)
+            native = {"value": m / (float(tn.item()) / 1e3), "unit": "predictions/s", "ms_per_step": float(tn.item()),
+                      "info": int(info_n.item()),
+                      "max_abs_pred_diff_vs_torch_distributed_sweep": float((pn - pred_dev).abs().max().item()),
+                      "max_abs_var_diff_vs_torch_distributed_sweep": float((vn - var).abs().max().item()),
+                      "local_GB": ns.local_bytes(N, m) / 1e9,
+                      "api": "ck_mg_create / ck_mg_joint_cov / ck_mg_potrf / ck_mg_potrs_predict (include/cokrig.h, csrc/ck_mgctx.cu)"}
+            assert native["info"] == 0 and native["max_abs_pred_diff_vs_torch_distributed_sweep"] < 1e-9 * float(pred_dev.abs().max().item())
+            ns.close()
+            del ns, pn, vn
+        except Exception as exc:  # noqa: BLE001  (an extra leg: never lose the line over it)
+            native = {"error": repr(exc)[:300]}
+        torch.cuda.empty_cache()
+
     # ---- N > 1: (a) the block-cyclic result against the single-GPU path (rank 0, untimed); (b) the independent-systems
     # number (one system per GPU, no collective) for reference
     replicas = None
@@ -613,6 +643,7 @@ def run_gpu(args, n_per_var: int, m: int) -> None:
         if strong:
             line["replicas"] = replicas
             line["parity_vs_single_gpu"] = parity
+            line["native_handle_api"] = native
         else:
             line["assembly_GBs"] = wm["bytes_assembled"] / ((phase_ms["assemble"] + phase_ms["cross"]) / 1e3) / 1e9
             line["cholesky_TFs"] = wm["potrf_flops"] / (phase_ms["potrf"] / 1e3) / 1e12
@@ -669,6 +700,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-dmma", action="store_true", help="skip the strict-FP64 (CK_OZAKI=0) step")
     ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel roofline entries of K1 / K2 / K4")
+    ap.add_argument("--no-native", action="store_true", help="N > 1: skip the leg through the C handle API (ck_mg_*)")
     ap.add_argument("--no-extras", action="store_true", help="N > 1: skip the single-GPU parity check and the replicas leg (tuning runs)")
     ap.add_argument("--grid", default="", help="process grid PxQ of the block-cyclic sweep (default: parallel.grid_shape)")
     ap.add_argument("--tile", type=int, default=1024, help="tile size of the block-cyclic sweep (N > 1)")

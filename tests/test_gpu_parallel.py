@@ -158,6 +158,6 @@ def test_two_gpus_under_torchrun():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs (run tools/mg_check.py under torchrun on a multi-GPU box)")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29533", os.path.join(ROOT, "tools", "mg_check.py"), "--points", "3000", "--targets", "1000", "--tile", "512"]
+           "--master-port", "29533", os.path.join(ROOT, "tools", "mg_check.py"), "--points", "3000", "--targets", "1000", "--tile", "512", "--native"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
