@@ -280,9 +280,11 @@ def update_kernel_roofline(achieved_int8: float, achieved_tf: float, fp64_flops:
          "peak_source": f"{n_gpus} x 2 x bf16_tflops_sustained ({ys['bf16_source']}); int8 dense = 2 x bf16 dense on sm_100a",
          "fp64_equiv_TFs": achieved_tf, "dgemm_live_TFs": ys["dgemm_TFs"], "fp64_equiv_over_dgemm": achieved_tf / (n_gpus * ys["dgemm_TFs"]),
          # ncu --set full of the largest update of the factorisation (rows = 38976, lower, K = 1024;
-         # profiles/r01ai_ozgemm_ncu_full_summary.txt): dram read 21.79 GB + write 6.08 GB; algorithmic 12.7 GB
-         "traffic": 27.86e9, "traffic_note": "per launch at rows=38976 (ncu r01ai), algorithmic 12.7e9 (C read + write 12.15e9, slices "
-                                             "0.56e9): operand slices re-read from DRAM (L2 hit rate 76 %)",
+         # profiles/r02x_ozgemm_l2hints3_ncu_full_summary.txt): dram read 19.15 GB + write 6.07 GB with the L2 eviction hints
+         # (22.41 + 6.07 GB without them, profiles/r02x_ozgemm_l2hints0_ncu_full_summary.txt); algorithmic 12.7 GB
+         "traffic": 25.22e9, "traffic_note": "per launch at rows=38976 (ncu r02x, CK_OZ_L2_HINTS=3: slices evict_last, C evict_first; "
+                                             "28.48e9 without the hints), algorithmic 12.7e9 (C read + write 12.15e9, slices 0.56e9): "
+                                             "operand slices re-read from DRAM (L2 hit rate 78 %); tensor pipe 80.3 % active",
          "flops_per_step": fp64_flops}
     if "int8_TOPs" in ys:
         r["int8_gemm_live_TOPs"] = {"burst": ys["int8_TOPs"], "sustained": ys["int8_TOPs_sustained"], "source": ys["int8_source"]}

@@ -573,7 +573,9 @@ static int oz_gemm_launch(const void* a_slices, const double* sa, ck_i64 m, cons
   static int hints_cfg = -1;
   if (hints_cfg < 0) {
     const char* e = getenv("CK_OZ_L2_HINTS");
-    hints_cfg = e ? (atoi(e) & 3) : 0;
+    // default 3 (both hints): measured on the C3 step 21 371 -> 21 536 predictions/s, the largest update alone 16.72 -> 15.79 ms
+    // (profiles/r02x_l2hints_sweep.log); 1: 21 483, 2: 21 411
+    hints_cfg = e ? (atoi(e) & 3) : 3;
   }
   g.l2_hints = hints_cfg;
   g.dbg = g_oz_dbg;
