@@ -29,6 +29,7 @@
 //                      time, 3 conversions + 2 FMAs in FP64, scale by s_a s_b (powers of two: exact) and C -= v.
 #include <stdint.h>
 #include <stdlib.h>
+#include <atomic>
 #include "ck_common.cuh"
 
 namespace {
@@ -43,6 +44,7 @@ constexpr int OZ_B_KU = OZ_S * OZ_TN * 16;     // 7168 B:  [q 7][row group 8][ro
 constexpr int OZ_B_STAGE = 2 * OZ_B_KU;        // 14336 B: [ku 2][...]
 constexpr int OZ_STAGE = OZ_A_STAGE + OZ_B_STAGE;
 constexpr int OZ_NSTAGE = 4;
+constexpr int OZ_NSCHED = 4;                   // depth of the tile-id ring of the dynamic scheduler
 constexpr int OZ_EPI_WARPS = 8;                // 2 per TMEM lane quadrant, 32 columns each
 constexpr int OZ_THREADS = 64 + 32 * OZ_EPI_WARPS;
 constexpr int OZ_TMEM_COLS = 512;
@@ -253,6 +255,9 @@ struct OzGemmArgs {
   long long gi0, gis, gj0, gjs;
   int vec;            // C is 16-byte aligned with an even leading dimension
   int l2_hints;       // bit 0: operand slices evict_last, bit 1: C loads / stores evict_first (CK_OZ_L2_HINTS)
+  // dynamic tile scheduler (CK_OZ_DYNAMIC, default on): sched[0] = next virtual tile (atomic counter), sched[1] = CTAs done;
+  // the last CTA to finish resets both, so a slot is 0 again when the launch ends.  NULL: static grid-stride assignment.
+  unsigned long long* sched;
   long long* dbg;     // optional per-CTA cycle counters (8 per CTA), see ck_oz_debug_buffer
 };
 
@@ -301,10 +306,16 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ck_oz_gemm_kernel(OzGemmArgs g)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)OZ_NSTAGE * OZ_STAGE);
   // bars[0..S) full, [S..2S) empty, [2S] tmem_full, [2S+1] tmem_empty (S = OZ_NSTAGE), then the TMEM base address
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * OZ_NSTAGE + 2);
+  // tile-id ring of the dynamic scheduler: the producer fetches the next virtual tile with one atomicAdd and hands (I, j) to the
+  // MMA thread and the epilogue warps; bars[2S+3 ..) = OZ_NSCHED full + OZ_NSCHED empty barriers, then the ids
+  int* tile_ring = reinterpret_cast<int*>(bars + 2 * OZ_NSTAGE + 3 + 2 * OZ_NSCHED);
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (OZ_NSTAGE + s); };
   const uint32_t tfull_bar = bar0 + 8u * (2 * OZ_NSTAGE), tempty_bar = bar0 + 8u * (2 * OZ_NSTAGE + 1);
+  auto sfull_bar = [&](int s) { return bar0 + 8u * (2 * OZ_NSTAGE + 3 + s); };
+  auto sempty_bar = [&](int s) { return bar0 + 8u * (2 * OZ_NSTAGE + 3 + OZ_NSCHED + s); };
+  const bool dyn = g.sched != nullptr;
   const uint32_t smem0 = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -315,6 +326,10 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ck_oz_gemm_kernel(OzGemmArgs g)
     }
     mbar_init(tfull_bar, 1);
     mbar_init(tempty_bar, 32 * OZ_EPI_WARPS);
+    for (int s = 0; s < OZ_NSCHED; ++s) {
+      mbar_init(sfull_bar(s), 1);
+      mbar_init(sempty_bar(s), 1 + OZ_EPI_WARPS);  // the MMA thread + one lane per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -334,9 +349,25 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ck_oz_gemm_kernel(OzGemmArgs g)
       int stage = 0;
       uint32_t phase = 0;
       const uint64_t pol = l2_policy((g.l2_hints & 1) ? 1 : 0);
-      for (long long t = blockIdx.x; t < g.nvirt; t += gridDim.x) {
-        int I, j;
-        if (!oz_decode(g, t, I, j)) continue;
+      int sslot = 0;
+      uint32_t sphase = 0;
+      for (long long t = blockIdx.x;; t += gridDim.x) {
+        int I = 0, j = 0;
+        if (dyn) {
+          // next valid tile in the global order: all CTAs stay inside one window of ~gridDim.x consecutive tiles (the
+          // A blocks of one super-row and a few B blocks: L2-resident), and nobody idles at the tail
+          do {
+            t = (long long)atomicAdd(g.sched, 1ULL);
+          } while (t < g.nvirt && !oz_decode(g, t, I, j));
+          mbar_wait(sempty_bar(sslot), sphase ^ 1u);
+          tile_ring[sslot] = t < g.nvirt ? ((I << 16) | j) : -1;
+          mbar_arrive(sfull_bar(sslot));
+          if (++sslot == OZ_NSCHED) { sslot = 0; sphase ^= 1u; }
+          if (t >= g.nvirt) break;
+        } else {
+          if (t >= g.nvirt) break;
+          if (!oz_decode(g, t, I, j)) continue;
+        }
         const uint8_t* ga = g.a + (size_t)I * g.kcn * OZ_A_STAGE;
         const uint8_t* gb = g.b + (size_t)j * g.kcn * OZ_B_STAGE;
         for (int kc = 0; kc < g.kcn; ++kc) {
@@ -360,9 +391,20 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ck_oz_gemm_kernel(OzGemmArgs g)
       const uint32_t a_lbo = 2048u, a_sbo = 128u;                // A slice: [ku][row group][8 rows][16 B]
       const uint32_t b_lbo = (uint32_t)OZ_B_KU, b_sbo = 128u;   // B k-unit: [q][row group][8 rows][16 B]
       const uint32_t id256 = umma_idesc_i8(256), id192 = umma_idesc_i8(192), id128 = umma_idesc_i8(128), id64 = umma_idesc_i8(64);
-      for (long long t = blockIdx.x; t < g.nvirt; t += gridDim.x) {
+      int sslot = 0;
+      uint32_t sphase = 0;
+      for (long long t = blockIdx.x;; t += gridDim.x) {
         int I, j;
-        if (!oz_decode(g, t, I, j)) continue;
+        if (dyn) {
+          mbar_wait(sfull_bar(sslot), sphase);
+          const int v = tile_ring[sslot];
+          mbar_arrive(sempty_bar(sslot));
+          if (++sslot == OZ_NSCHED) { sslot = 0; sphase ^= 1u; }
+          if (v < 0) break;
+        } else {
+          if (t >= g.nvirt) break;
+          if (!oz_decode(g, t, I, j)) continue;
+        }
         long long w0 = clock64();
         mbar_wait(tempty_bar, aphase ^ 1u);
         tc_fence_after();
@@ -412,9 +454,23 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ck_oz_gemm_kernel(OzGemmArgs g)
     uint32_t aphase = 0;
     const uint64_t cpol = l2_policy((g.l2_hints & 2) ? 2 : 0);
     long long t_busy = 0, t_wait = 0;
-    for (long long t = blockIdx.x; t < g.nvirt; t += gridDim.x) {
+    int sslot = 0;
+    uint32_t sphase = 0;
+    for (long long t = blockIdx.x;; t += gridDim.x) {
       int I, j;
-      if (!oz_decode(g, t, I, j)) continue;
+      if (dyn) {
+        mbar_wait(sfull_bar(sslot), sphase);
+        const int v = tile_ring[sslot];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sempty_bar(sslot));
+        if (++sslot == OZ_NSCHED) { sslot = 0; sphase ^= 1u; }
+        if (v < 0) break;
+        I = v >> 16;
+        j = v & 0xffff;
+      } else {
+        if (t >= g.nvirt) break;
+        if (!oz_decode(g, t, I, j)) continue;
+      }
       const long long row = (long long)I * OZ_TM + 32 * qd + lane;
       const long long cb = (long long)j * OZ_TN + EC * half;
       const bool row_ok = row < g.m;
@@ -487,6 +543,14 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ck_oz_gemm_kernel(OzGemmArgs g)
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)OZ_TMEM_COLS) : "memory");
   }
+  if (dyn && threadIdx.x == 0) {
+    // every CTA has fetched its last tile before it gets here: the last one to arrive leaves the slot zeroed for its next user
+    if (atomicAdd(g.sched + 1, 1ULL) == (unsigned long long)gridDim.x - 1ULL) {
+      g.sched[0] = 0ULL;
+      g.sched[1] = 0ULL;
+      __threadfence();
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -519,6 +583,8 @@ extern "C" int ck_oz_split(const double* src, ck_i64 ld, ck_i64 rows, ck_i64 k, 
   CK_LAUNCH_CHECK();
   return CK_OK;
 }
+
+__device__ unsigned long long g_oz_sched_slots[2 * 64];  // dynamic tile scheduler: (next tile, CTAs done) x 64 launches in flight
 
 static long long* g_oz_dbg = nullptr;
 extern "C" int ck_oz_debug_buffer(void* dev_counters) {
@@ -578,6 +644,27 @@ static int oz_gemm_launch(const void* a_slices, const double* sa, ck_i64 m, cons
     hints_cfg = e ? (atoi(e) & 3) : 3;
   }
   g.l2_hints = hints_cfg;
+  static int dyn_cfg = -1;
+  if (dyn_cfg < 0) {
+    const char* e = getenv("CK_OZ_DYNAMIC");
+    dyn_cfg = e ? (atoi(e) != 0) : 1;
+  }
+  g.sched = nullptr;
+  if (dyn_cfg && g.ni < 32768 && g.nj < 65536) {
+    // one counter pair per launch in flight, taken round-robin from 64 statically allocated device slots (no allocation);
+    // a slot is zero again when its launch has ended, and 64 launches of this kernel are never in flight at once
+    static unsigned long long* base[64] = {};
+    static std::atomic<unsigned> seq{0};
+    int dev = 0;
+    CK_CUDA(cudaGetDevice(&dev));
+    CK_REQUIRE(dev >= 0 && dev < 64, "device index %d out of range", dev);
+    if (!base[dev]) {
+      void* ptr = nullptr;
+      CK_CUDA(cudaGetSymbolAddress(&ptr, g_oz_sched_slots));
+      base[dev] = static_cast<unsigned long long*>(ptr);
+    }
+    g.sched = base[dev] + 2 * (seq.fetch_add(1, std::memory_order_relaxed) % 64u);
+  }
   g.dbg = g_oz_dbg;
   long long grid = oz_num_sms();
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;  // caller leaves SMs to a concurrent stream (look-ahead)
