@@ -634,6 +634,15 @@ static int oz_la_sms() {
   }
   return v;
 }
+// CK_OZ_PRESPLIT (default 1): split the next panel on the side stream, one step ahead (two scratch sets)
+static int oz_presplit() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CK_OZ_PRESPLIT");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v;
+}
 static ck_i64 oz_la_min_rows() {
   static ck_i64 v = -1;
   if (v < 0) {
@@ -657,8 +666,14 @@ struct OzScratch {
 // sized under one configuration stays valid under any other.
 constexpr ck_i64 OZ_WS_MIN_N = 2048;
 static bool oz_wanted(ck_i64 n) { return oz_enabled() && n >= OZ_WS_MIN_N && n >= 2 * oz_min_rows(); }
-static OzScratch oz_scratch(void* ws, ck_i64 n) {
-  char* p = static_cast<char*>(ws) + xinv_bytes(n);
+static size_t oz_scratch_bytes(ck_i64 n) {
+  return align256(ck_oz_slices_bytes(n, OZ_KMAX, 0)) + align256(ck_oz_slices_bytes(n, OZ_KMAX, 1)) +
+         2 * align256((size_t)ck_oz_scales_len(n) * sizeof(double));
+}
+// two sets (which = 0 / 1): while the update of aggregate j reads one, the side stream splits the finished panel of
+// aggregate j + 1 into the other (the split is then off the main stream's critical path)
+static OzScratch oz_scratch(void* ws, ck_i64 n, int which = 0) {
+  char* p = static_cast<char*>(ws) + xinv_bytes(n) + (size_t)which * oz_scratch_bytes(n);
   OzScratch s;
   s.fa = p; p += align256(ck_oz_slices_bytes(n, OZ_KMAX, 0));
   s.fb = p; p += align256(ck_oz_slices_bytes(n, OZ_KMAX, 1));
@@ -672,9 +687,7 @@ extern "C" int ck_oz_active(ck_i64 n) { return (oz_wanted(n) && (ck_i64)agg_bloc
 extern "C" size_t ck_potrf_workspace_bytes(ck_i64 n) {
   if (n <= 0) return 0;
   size_t b = xinv_bytes(n);
-  if (n >= OZ_WS_MIN_N)
-    b += align256(ck_oz_slices_bytes(n, OZ_KMAX, 0)) + align256(ck_oz_slices_bytes(n, OZ_KMAX, 1)) +
-         2 * align256((size_t)ck_oz_scales_len(n) * sizeof(double));
+  if (n >= OZ_WS_MIN_N) b += 2 * oz_scratch_bytes(n);
   return b;
 }
 
@@ -817,7 +830,9 @@ extern "C" int ck_potrf(double* a, ck_i64 n, ck_i64 ld, void* ws, int* info, voi
   if (oz_wanted(n) && (ck_i64)agg * CK_NB <= OZ_KMAX) {
     // Big trailing updates on the INT8 tensor cores: per aggregate, the panel chain (FP64 DMMA, recursive), one split
     // of the finished panel into digit slices, one persistent tcgen05 kernel over the lower tiles of the trailing matrix.
-    const OzScratch z = oz_scratch(ws, n);
+    const OzScratch zs[2] = {oz_scratch(ws, n, 0), oz_scratch(ws, n, 1)};
+    int cur = 0;
+    bool have = false;  // zs[cur] already holds the slices of the current panel (split on the side stream, one step ahead)
     const int la = oz_la_sms();
     SideStream* oside = nullptr;
     if (la > 0 && lookahead_enabled() && n >= 2 * oz_la_min_rows()) {
@@ -837,15 +852,24 @@ extern "C" int ck_potrf(double* a, ck_i64 n, ck_i64 ld, void* ws, int* info, voi
       const ck_i64 rows = n - k1, kk = k1 - k0, off = k2 - k1;
       const bool use_oz = rows >= oz_min_rows() && kk % 32 == 0;
       const bool la_now = oside && use_oz && (n - k2) >= oz_la_min_rows() && off % 128 == 0;
-      if (use_oz) {
+      const OzScratch z = zs[cur];
+      if (use_oz && !have) {
         if ((rc = ck_oz_split(a + k1 * ld + k0, ld, rows, kk, z.fa, z.fb, z.sa, stream))) return rc;
       }
+      have = false;
       if (la_now) {
         // (a) columns of the next aggregate: A[k1:, k1:k2] -= P P[k1:k2]^T  (every SM)
         if ((rc = ck_oz_gemm(z.fa, z.sa, rows, z.fb, z.sa, off, kk, a + k1 * ld + k1, ld, 1, 0, stream))) return rc;
         CK_CUDA(cudaEventRecord(oside->ev_a, st));
         CK_CUDA(cudaStreamWaitEvent(oside->s, oside->ev_a, 0));
         if ((rc = factor_range(ocs, b1, b2))) return rc;  // panel chain of the next aggregate, beside (b)
+        if (oz_presplit() && k2 < n && n - k2 >= oz_min_rows() && off % 32 == 0) {
+          // ... and the split of that panel into the OTHER scratch set (its last reader, update (b) of the previous step,
+          // finished before (a) of this one): the next step starts with its slices ready
+          const OzScratch zn = zs[cur ^ 1];
+          if ((rc = ck_oz_split(a + k2 * ld + k1, ld, n - k2, off, zn.fa, zn.fb, zn.sa, oside->s))) return rc;
+          have = true;
+        }
         CK_CUDA(cudaEventRecord(oside->ev_c, oside->s));
         // (b) the rest: A[k2:, k2:] -= P[k2:] P[k2:]^T on all but `la` SMs
         const char* fa2 = static_cast<const char*>(z.fa) + (size_t)(off / 128) * ck_oz_slices_bytes(128, kk, 0);
@@ -867,6 +891,7 @@ extern "C" int ck_potrf(double* a, ck_i64 n, ck_i64 ld, void* ws, int* info, voi
         }
         if ((rc = factor_range(c, b1, b2))) return rc;
       }
+      if (have) cur ^= 1;
     }
     return CK_OK;
   }
@@ -1036,7 +1061,9 @@ extern "C" int ck_trsm_lower(const double* l, ck_i64 n, ck_i64 ld, const void* w
   if (oz_wanted(n) && (ck_i64)agg * CK_NB <= OZ_KMAX && nrhs >= 1024 && nrhs <= n) {
     // INT8 tensor-core updates (see ck_potrf).  The slice scratch lives behind the block inverses in the
     // factorisation workspace: solves that share one factor must not run concurrently.
-    const OzScratch z = oz_scratch(const_cast<void*>(ws), n);
+    const OzScratch zs[2] = {oz_scratch(const_cast<void*>(ws), n, 0), oz_scratch(const_cast<void*>(ws), n, 1)};
+    int cur = 0;
+    bool have = false;  // zs[cur] already holds the slices of V[:, k0:k1] and L[k1:, k0:k1] (split on the side stream)
     const int la = oz_la_sms();
     SideStream* oside = nullptr;
     if (la > 0 && lookahead_enabled() && n >= 2 * oz_la_min_rows()) {
@@ -1056,16 +1083,27 @@ extern "C" int ck_trsm_lower(const double* l, ck_i64 n, ck_i64 ld, const void* w
       const ck_i64 cols = n - k1, kk = k1 - k0, off = k2 - k1;
       const bool use_oz = cols >= oz_min_rows() && kk % 32 == 0;
       const bool la_now = oside && use_oz && (n - k2) >= oz_la_min_rows() && off % 64 == 0;
-      if (use_oz) {
+      const OzScratch z = zs[cur];
+      if (use_oz && !have) {
         if ((rc = ck_oz_split(rhs + k0, ld_rhs, nrhs, kk, z.fa, nullptr, z.sa, stream))) return rc;
         if ((rc = ck_oz_split(l + k1 * ld + k0, ld, cols, kk, nullptr, z.fb, z.sb, stream))) return rc;
       }
+      have = false;
       if (la_now) {
         // (a) columns of the next aggregate: R[:, k1:k2] -= V L[k1:k2]^T  (every SM)
         if ((rc = ck_oz_gemm(z.fa, z.sa, nrhs, z.fb, z.sb, off, kk, rhs + k1, ld_rhs, 0, 0, stream))) return rc;
         CK_CUDA(cudaEventRecord(oside->ev_a, st));
         CK_CUDA(cudaStreamWaitEvent(oside->s, oside->ev_a, 0));
+        const bool presplit = oz_presplit() && k2 < n && n - k2 >= oz_min_rows() && off % 32 == 0;
+        const OzScratch zn = zs[cur ^ 1];
+        if (presplit) {  // the next L panel is final already: split it first, then the small solves, then their result
+          if ((rc = ck_oz_split(l + k2 * ld + k1, ld, n - k2, off, nullptr, zn.fb, zn.sb, oside->s))) return rc;
+        }
         if ((rc = solve_range(ocs, b1, b2))) return rc;  // small solves of the next aggregate, beside (b)
+        if (presplit) {
+          if ((rc = ck_oz_split(rhs + k1, ld_rhs, nrhs, off, zn.fa, nullptr, zn.sa, oside->s))) return rc;
+          have = true;
+        }
         CK_CUDA(cudaEventRecord(oside->ev_c, oside->s));
         // (b) the rest: R[:, k2:] -= V L[k2:]^T on all but `la` SMs
         const char* fb2 = static_cast<const char*>(z.fb) + (size_t)(off / 64) * ck_oz_slices_bytes(64, kk, 1);
@@ -1086,6 +1124,7 @@ extern "C" int ck_trsm_lower(const double* l, ck_i64 n, ck_i64 ld, const void* w
         }
         if ((rc = solve_range(c, b1, b2))) return rc;
       }
+      if (have) cur ^= 1;
     }
     return CK_OK;
   }
