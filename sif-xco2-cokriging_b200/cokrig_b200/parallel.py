@@ -371,10 +371,13 @@ class BlockCyclicCokriging:
         w_main = rows * cols / (2.0 * g.P * g.Q)
         w_panel = 2.0 * max(self.TR - k - 2, 0) / g.P
         tau, fixed = 3.65 * (self.tb / 1024.0) ** 3, 1.7
-        best, best_t = 40, float("inf")
-        # never below 40: the NCCL kernels of the look-ahead broadcasts occupy SMs of their own, and a persistent update kernel
-        # whose CTAs cannot all be resident at launch finishes late (static tile partition; measured: profiles/r02_mg_trace_*)
-        for r in range(40, nsm - 23, 4):
+        # floor 24 (CK_MG_PANEL_MIN): measured on C3 / 2 GPUs with the dynamically scheduled update kernel 16 -> 254.9 ms,
+        # 24 -> 247.4, 32 -> 248.2, 40 -> 253.7 (profiles/r02z_mg_panel_min_sweep_2gpu.log); with the static tile partition of
+        # round 1 anything below 40 lost time (an update kernel whose CTAs are not all resident at launch finished late)
+        floor = int(os.environ.get("CK_MG_PANEL_MIN", "24"))
+        best, best_t = floor, float("inf")
+        # the NCCL kernels of the look-ahead broadcasts occupy SMs of their own, hence a floor
+        for r in range(floor, nsm - 23, 4):
             t = max(w_main * tau / (nsm - r), w_panel * tau / r + fixed)
             if t < best_t:
                 best, best_t = r, t

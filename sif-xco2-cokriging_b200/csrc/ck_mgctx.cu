@@ -145,7 +145,7 @@ struct ck_mg_ctx {
   int world = 1, rank = 0, P = 1, Q = 1, p = 0, q = 0;
   ck_i64 tb = 1024;
   int device = 0, nsm = 148;
-  int lookahead = 1, panel_sms_fixed = -1, int8_min_tiles = 600;
+  int lookahead = 1, panel_sms_fixed = -1, int8_min_tiles = 600, panel_min = 24;  // floor of the panel stream's SM share: see parallel._panel_share
   ncclComm_t comm_world = nullptr, comm_row = nullptr, comm_col = nullptr;
   cudaStream_t panel = nullptr;
   cudaEvent_t tev[4] = {};
@@ -282,9 +282,9 @@ int panel_share(const ck_mg_ctx* h, ck_i64 k) {
   const double w_main = rows * cols / (2.0 * h->P * h->Q);
   const double w_panel = 2.0 * (double)(h->TR - k - 2 > 0 ? h->TR - k - 2 : 0) / h->P;
   const double s = (double)h->tb / 1024.0, tau = 3.65 * s * s * s, fixed = 1.7;
-  int best = 40;
+  int best = h->panel_min;
   double best_t = 1e300;
-  for (int r = 40; r < h->nsm - 23; r += 4) {
+  for (int r = h->panel_min; r < h->nsm - 23; r += 4) {
     const double a = w_main * tau / (h->nsm - r), b = w_panel * tau / r + fixed;
     const double t = a > b ? a : b;
     if (t < best_t) best_t = t, best = r;
@@ -416,6 +416,7 @@ extern "C" int ck_mg_create(ck_mg_ctx** out, int world, int rank, int P, int Q, 
   if (const char* e = getenv("CK_MG_LOOKAHEAD")) h->lookahead = atoi(e) != 0;
   if (const char* e = getenv("CK_MG_PANEL_SMS")) h->panel_sms_fixed = atoi(e);
   if (const char* e = getenv("CK_MG_INT8_MIN_TILES")) h->int8_min_tiles = atoi(e);
+  if (const char* e = getenv("CK_MG_PANEL_MIN")) h->panel_min = atoi(e) > 4 ? atoi(e) : 4;
   int lo = 0, hi = 0;
   if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess ||
       cudaStreamCreateWithPriority(&h->panel, cudaStreamNonBlocking, hi) != cudaSuccess) {
