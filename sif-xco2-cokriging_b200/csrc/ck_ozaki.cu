@@ -29,7 +29,7 @@
 //                      time, 3 conversions + 2 FMAs in FP64, scale by s_a s_b (powers of two: exact) and C -= v.
 #include <stdint.h>
 #include <stdlib.h>
-#include <atomic>
+#include <mutex>
 #include "ck_common.cuh"
 
 namespace {
@@ -256,7 +256,7 @@ struct OzGemmArgs {
   int vec;            // C is 16-byte aligned with an even leading dimension
   int l2_hints;       // bit 0: operand slices evict_last, bit 1: C loads / stores evict_first (CK_OZ_L2_HINTS)
   // dynamic tile scheduler (CK_OZ_DYNAMIC, default on): sched[0] = next virtual tile (atomic counter), sched[1] = CTAs done;
-  // the last CTA to finish resets both, so a slot is 0 again when the launch ends.  NULL: static grid-stride assignment.
+  // the last CTA to finish resets both, so the stream's slot is 0 again when the launch ends.  NULL: static grid-stride assignment.
   unsigned long long* sched;
   long long* dbg;     // optional per-CTA cycle counters (8 per CTA), see ck_oz_debug_buffer
 };
@@ -584,7 +584,8 @@ extern "C" int ck_oz_split(const double* src, ck_i64 ld, ck_i64 rows, ck_i64 k, 
   return CK_OK;
 }
 
-__device__ unsigned long long g_oz_sched_slots[2 * 64];  // dynamic tile scheduler: (next tile, CTAs done) x 64 launches in flight
+constexpr int OZ_SCHED_SLOTS = 256;
+__device__ unsigned long long g_oz_sched_slots[2 * OZ_SCHED_SLOTS];  // dynamic tile scheduler: (next tile, CTAs done) per stream
 
 static long long* g_oz_dbg = nullptr;
 extern "C" int ck_oz_debug_buffer(void* dev_counters) {
@@ -651,19 +652,36 @@ static int oz_gemm_launch(const void* a_slices, const double* sa, ck_i64 m, cons
   }
   g.sched = nullptr;
   if (dyn_cfg && g.ni < 32768 && g.nj < 65536) {
-    // one counter pair per launch in flight, taken round-robin from 64 statically allocated device slots (no allocation);
-    // a slot is zero again when its launch has ended, and 64 launches of this kernel are never in flight at once
+    // One counter pair per (device, stream), from statically allocated device slots (no allocation): launches on one stream
+    // never overlap and every launch leaves its slot zeroed, so a stream can reuse its slot for ever, while launches on
+    // different streams (look-ahead beside the trailing update, batched windows) never share one.  More than OZ_SCHED_SLOTS
+    // streams on a device: the extra streams fall back to the static assignment.
+    struct Slot { int dev; cudaStream_t st; };
+    static Slot tab[OZ_SCHED_SLOTS];
+    static int used = 0;
     static unsigned long long* base[64] = {};
-    static std::atomic<unsigned> seq{0};
+    static std::mutex mu;
     int dev = 0;
     CK_CUDA(cudaGetDevice(&dev));
     CK_REQUIRE(dev >= 0 && dev < 64, "device index %d out of range", dev);
+    cudaStream_t cst = ck_stream(stream);
+    std::lock_guard<std::mutex> lock(mu);
     if (!base[dev]) {
       void* ptr = nullptr;
       CK_CUDA(cudaGetSymbolAddress(&ptr, g_oz_sched_slots));
       base[dev] = static_cast<unsigned long long*>(ptr);
     }
-    g.sched = base[dev] + 2 * (seq.fetch_add(1, std::memory_order_relaxed) % 64u);
+    int idx = -1, on_dev = 0;
+    for (int i = 0; i < used; ++i) {
+      if (tab[i].dev != dev) continue;
+      if (tab[i].st == cst) { idx = on_dev; break; }
+      ++on_dev;
+    }
+    if (idx < 0 && on_dev < OZ_SCHED_SLOTS && used < OZ_SCHED_SLOTS) {
+      tab[used++] = Slot{dev, cst};
+      idx = on_dev;
+    }
+    if (idx >= 0) g.sched = base[dev] + 2 * idx;  // idx = rank of this stream among the streams seen on this device
   }
   g.dbg = g_oz_dbg;
   long long grid = oz_num_sms();
