@@ -214,3 +214,41 @@ def test_factor_and_solve_at_scale_with_lookahead(lib):
         lib.lib.ck_oz_configure(1, -1)
     assert (fd.lower() - L).abs().max().item() / L.abs().max().item() < 1e-13
     assert (Vd - V).abs().max().item() / V.abs().max().item() < 1e-11
+
+
+def test_concurrent_streams_share_no_scheduler_state(lib):
+    """Batched windows (BASELINE config 4): several factorisations + solves enqueued on different CUDA streams run their
+    INT8 update kernels side by side.  Each launch's dynamic tile scheduler draws from a counter slot that belongs to its
+    (device, stream), so the concurrent results must equal -- bit for bit -- the ones computed alone on the default stream."""
+    import torch
+    from cokrig_b200 import METRIC_EUCLID, ops
+    n, m, nsys = 1536, 700, 6   # N = 3072 per system: trailing updates on the INT8 path (>= 2048 rows)
+    params = [1, .8, 1.5, 1.5, 1.5, .07, .07, .07, .02, .02, -.2]
+    assert lib.lib.ck_oz_active(2 * n) == 1
+    systems = []
+    for s in range(nsys):
+        rng = np.random.default_rng(100 + s)
+        xy = ops.coords_to_device(rng.uniform(0, 1, (n, 2)))
+        B = ops.to_device(rng.standard_normal((m, 2 * n)))
+        systems.append((ops.joint_cov([xy, xy], params, 2, METRIC_EUCLID), B))
+
+    def run(S0, B):
+        f = ops.potrf(S0.clone())
+        rb = torch.empty((m, ops.padded_ld(2 * n)), dtype=torch.float64, device="cuda")[:, : 2 * n]
+        rb.copy_(B)
+        return f, f.solve_lower(rb)
+
+    alone = [run(S0, B) for S0, B in systems]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in range(3)]
+    for rep in range(2):
+        together = []
+        for s, (S0, B) in enumerate(systems):
+            st = streams[s % len(streams)]
+            st.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(st):
+                together.append(run(S0, B))
+        torch.cuda.synchronize()
+        for (f1, v1), (f2, v2) in zip(alone, together):
+            assert f2.info == 0
+            assert torch.equal(torch.tril(f1.L), torch.tril(f2.L)) and torch.equal(v1, v2)
