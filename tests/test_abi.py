@@ -142,3 +142,29 @@ def test_multi_gpu_handle_api_argument_checks_without_a_device():
     assert lib.ck_mg_workspace_bytes(None, 10, 10) == 0
     assert lib.ck_mg_destroy(None) == _lib.CK_OK
     assert lib.ck_mg_potrf(None, None) == _lib.CK_ERR_ARG
+
+
+def test_header_and_c_example_compile_as_plain_c(tmp_path):
+    """include/cokrig.h is a C header (C99, no C++), and examples/mg_cokrige.c -- the multi-GPU sweep driven from plain C --
+    compiles and links against the library; without a GPU the program reports so and exits 1 (no CPU fallback)."""
+    import shutil
+    import subprocess
+    from cokrig_b200 import _lib
+    if not shutil.which("gcc"):
+        pytest.skip("gcc not available")
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "cokrig.h"\nint main(void) { return ck_version() > 0 ? 0 : 1; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-fsyntax-only", str(src)])
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    if not os.path.exists(os.path.join(cuda, "include", "cuda_runtime.h")):
+        pytest.skip("CUDA toolkit headers not found")
+    exe = tmp_path / "mg_cokrige"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(cuda, "include"),
+                           os.path.join(ROOT, "examples", "mg_cokrige.c"), "-L", libdir, "-lcokrig_b200", "-L", os.path.join(cuda, "lib64"),
+                           "-lcudart", "-lm", "-o", str(exe)])
+    import torch
+    if not torch.cuda.is_available():
+        env = dict(os.environ, LD_LIBRARY_PATH=libdir + ":" + os.path.join(cuda, "lib64") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+        r = subprocess.run([str(exe), "0", "1"], env=env, capture_output=True, text=True)
+        assert r.returncode == 1 and "no CUDA device" in r.stderr

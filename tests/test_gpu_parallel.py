@@ -129,6 +129,42 @@ def test_native_handle_api_int8_updates_and_non_pd():
     plain.close()
 
 
+def test_c_example_program_vs_oracle(tmp_path):
+    """examples/mg_cokrige.c: a plain C99 host (no Python, no torch in the process) drives ck_mg_* and must print the
+    oracle's predictions for the same inputs (libc rand() stream reproduced through ctypes)."""
+    import ctypes
+    import re
+    import shutil
+    from cokrig_b200 import _lib
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    if not shutil.which("gcc") or not os.path.exists(os.path.join(cuda, "include", "cuda_runtime.h")):
+        pytest.skip("gcc / CUDA headers not available")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    exe = str(tmp_path / "mg_cokrige")
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(cuda, "include"),
+                           os.path.join(ROOT, "examples", "mg_cokrige.c"), "-L", libdir, "-lcokrig_b200", "-L", os.path.join(cuda, "lib64"),
+                           "-lcudart", "-lm", "-o", exe])
+    n0, n1, m = 1500, 1400, 300
+    import torch
+    tl = os.path.join(os.path.dirname(torch.__file__), "lib")
+    env = dict(os.environ, LD_LIBRARY_PATH=":".join([libdir, os.path.join(cuda, "lib64"), tl, os.environ.get("LD_LIBRARY_PATH", "")]))
+    r = subprocess.run([exe, "0", "1", "/tmp/unused", str(n0), str(n1), str(m)], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = [float(v) for v in re.search(r"pred\[0\.\.3\] = ([-0-9.e ]+);", r.stdout).group(1).split()]
+    logdet = float(re.search(r"logdet ([-0-9.e]+)", r.stdout).group(1))
+    libc = ctypes.CDLL("libc.so.6")
+    libc.srand(7)
+    h = np.array([libc.rand() for _ in range(2 * (n0 + n1 + m) + n0 + n1)], dtype=np.float64) / 2147483647.0
+    xy0, xy1 = h[: 2 * n0].reshape(n0, 2), h[2 * n0: 2 * (n0 + n1)].reshape(n1, 2)
+    xyp = h[2 * (n0 + n1): 2 * (n0 + n1 + m)].reshape(m, 2)
+    z = h[2 * (n0 + n1 + m):]
+    params = [1.0, 0.8, 1.5, 1.5, 1.5, 0.1, 0.1, 0.1, 0.02, 0.02, -0.2]
+    rp, _, _ = orc.joint_predict(orc.Params(params), 0, [xy0, xy1], [z[:n0], z[n0:]], xyp, "euclidean")
+    assert np.max(np.abs(np.array(got) - rp[:4])) < 1e-9 * np.max(np.abs(rp))
+    sigma = orc.joint_cov(orc.Params(params), [xy0, xy1], "euclidean")
+    assert abs(logdet / np.linalg.slogdet(sigma)[1] - 1) < 1e-9
+
+
 def test_block_cyclic_single_rank_reports_non_pd():
     from cokrig_b200 import parallel
     coords, z, targets = _inputs(0, 300, 280, 20, 2)
