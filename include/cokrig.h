@@ -393,6 +393,14 @@ int ck_oz_gemm(const void* a_slices_dev, const double* a_scales_dev, ck_i64 m, c
                const double* b_scales_dev, ck_i64 n, ck_i64 k, double* c_dev, ck_i64 ldc, int lower, int max_ctas,
                void* stream);
 
+/* HOST-ONLY (no CUDA call): the order in which ck_oz_gemm (tb == 0) / ck_oz_mg_update (tb > 0) visit the 128 x 64 tiles of C
+ * for a problem shape -- what the kernel's dynamic scheduler hands out.  Writes up to `cap` (row block I, column block j)
+ * pairs to ij_out and, per tile, the largest column its first row may update (-1: unmasked) to col_limits_out (either may
+ * be NULL); *nvirt_out = virtual tiles including the skipped ones.  Returns the number of tiles visited, -1 on bad arguments. */
+ck_i64 ck_oz_tile_order(ck_i64 m, ck_i64 n, int lower, ck_i64 tb, ck_i64 row_tile0, ck_i64 row_tile_step, ck_i64 col_tile0,
+                        ck_i64 col_tile_step, int* ij_out /*HOST*/, ck_i64 cap, ck_i64* nvirt_out /*HOST*/,
+                        ck_i64* col_limits_out /*HOST*/);
+
 /* The same product with the masking contract of ck_mg_update: C is the local part of a 2-D block-cyclic matrix (square
  * tiles of tb elements, local tile (li, lj) = global tile (row_tile0 + li row_tile_step, col_tile0 + lj col_tile_step));
  * tiles with J > I are skipped, tiles with J == I keep their lower triangle.  m, n whole tiles. */

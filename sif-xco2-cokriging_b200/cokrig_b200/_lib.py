@@ -98,6 +98,8 @@ SIGNATURES = {
     "ck_oz_split": (c_int, [_dp, c_int64, c_int64, c_int64, _dp, _dp, _dp, c_void_p]),
     "ck_oz_mg_update": (c_int, [_dp, _dp, c_int64, _dp, _dp, c_int64, c_int64, _dp, c_int64, c_int64, c_int64, c_int64, c_int64,
                                 c_int64, c_int, c_void_p]),
+    "ck_oz_tile_order": (c_int64, [c_int64, c_int64, c_int, c_int64, c_int64, c_int64, c_int64, c_int64, POINTER(c_int), c_int64,
+                                   POINTER(c_int64), POINTER(c_int64)]),
     "ck_oz_gemm": (c_int, [_dp, _dp, c_int64, _dp, _dp, c_int64, c_int64, _dp, c_int64, c_int, c_int, c_void_p]),
     "ck_vario_bin_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int]),
     "ck_vario_bin": (c_int, [_dp, _dp, c_int64, c_double, _dp, _dp, c_int64, c_double, c_int, c_int, c_int,

@@ -263,7 +263,7 @@ struct OzGemmArgs {
 
 // virtual tile t -> (I, j).  Tiles are ordered in super-rows of sr (default 16, CK_OZ_SUPER_ROWS) row blocks, inside a
 // super-row column-major (j outer, I inner), so that the ~148 tiles in flight share 16 A blocks and ~9 B blocks (L2 reuse).
-__device__ __forceinline__ bool oz_decode(const OzGemmArgs& g, long long t, int& I, int& j) {
+__host__ __device__ __forceinline__ bool oz_decode(const OzGemmArgs& g, long long t, int& I, int& j) {
   long long s, u;
   const long long sr = g.sr;  // row blocks per super-row
   if (g.tri) {
@@ -291,7 +291,7 @@ __device__ __forceinline__ bool oz_decode(const OzGemmArgs& g, long long t, int&
 }
 
 // largest column of C that row `row` may update inside column block j (LLONG_MAX: no mask)
-__device__ __forceinline__ long long oz_col_limit(const OzGemmArgs& g, long long row, int j) {
+__host__ __device__ __forceinline__ long long oz_col_limit(const OzGemmArgs& g, long long row, int j) {
   if (g.tb) {
     const long long li = row / g.tb, lj = ((long long)j * OZ_TN) / g.tb;
     const long long Ig = g.gi0 + li * g.gis, Jg = g.gj0 + lj * g.gjs;
@@ -604,22 +604,9 @@ static int oz_num_sms() {
 }
 int ck_oz_num_sms() { return oz_num_sms(); }
 
-static int oz_gemm_launch(const void* a_slices, const double* sa, ck_i64 m, const void* b_slices, const double* sb, ck_i64 n,
-                          ck_i64 k, double* c, ck_i64 ldc, int lower, ck_i64 tb, ck_i64 gi0, ck_i64 gis, ck_i64 gj0, ck_i64 gjs,
-                          int max_ctas, void* stream) {
-  CK_REQUIRE(m >= 0 && n >= 0 && k >= 0, "negative size");
-  if (m == 0 || n == 0 || k == 0) return CK_OK;
-  CK_REQUIRE(a_slices && b_slices && sa && sb && c, "null pointer");
-  CK_REQUIRE(k % OZ_KC == 0 && k <= 1024, "k (%lld) must be a multiple of 32 and <= 1024", (long long)k);
-  CK_REQUIRE(ldc >= n, "ldc (%lld) < n (%lld)", (long long)ldc, (long long)n);
-  CK_REQUIRE((((uintptr_t)a_slices | (uintptr_t)b_slices) & 15) == 0, "slice buffers must be 16-byte aligned");
-  static CkPerDevice attr;
-  CK_SET_SMEM_ONCE(attr, ck_oz_gemm_kernel, OZ_SMEM);
-  OzGemmArgs g;
-  g.a = static_cast<const uint8_t*>(a_slices);
-  g.b = static_cast<const uint8_t*>(b_slices);
-  g.sa = sa; g.sb = sb; g.c = c; g.ldc = ldc; g.m = m; g.n = n;
-  g.kcn = (int)(k / OZ_KC);
+// tile space of one launch: row / column blocks, masks, and the virtual tile order (super-rows, column-major inside)
+static void oz_geometry(OzGemmArgs& g, ck_i64 m, ck_i64 n, int lower, ck_i64 tb, ck_i64 gi0, ck_i64 gis, ck_i64 gj0, ck_i64 gjs) {
+  g.m = m; g.n = n;
   g.ni = (int)((m + OZ_TM - 1) / OZ_TM);
   g.nj = (int)((n + OZ_TN - 1) / OZ_TN);
   g.lower = (lower && !tb) ? 1 : 0;
@@ -636,6 +623,51 @@ static int oz_gemm_launch(const void* a_slices, const double* sa, ck_i64 m, cons
   // lower updates, the rectangular space otherwise
   g.tri = (g.lower && (long long)g.nj >= 2LL * g.ni - 1) ? 1 : 0;
   g.nvirt = g.tri ? (long long)g.sr * g.sr * srows * (srows + 1) : srows * (long long)g.sr * g.nj;
+}
+
+// Host-only: the order in which the update kernel visits the tiles of a problem shape (what the dynamic scheduler hands
+// out), for the CPU test tier -- every tile that must be updated appears exactly once, no masked tile appears.
+extern "C" ck_i64 ck_oz_tile_order(ck_i64 m, ck_i64 n, int lower, ck_i64 tb, ck_i64 row_tile0, ck_i64 row_tile_step, ck_i64 col_tile0,
+                                   ck_i64 col_tile_step, int* ij_out, ck_i64 cap, ck_i64* nvirt_out, ck_i64* col_limits_out) {
+  if (m <= 0 || n <= 0 || (tb && (tb % 128 || m % tb || n % tb)) || row_tile_step < 1 || col_tile_step < 1) return -1;
+  OzGemmArgs g = {};
+  oz_geometry(g, m, n, lower, tb, row_tile0, row_tile_step, col_tile0, col_tile_step);
+  if (nvirt_out) *nvirt_out = g.nvirt;
+  ck_i64 count = 0;
+  for (long long t = 0; t < g.nvirt; ++t) {
+    int I, j;
+    if (!oz_decode(g, t, I, j)) continue;
+    if (ij_out && count < cap) {
+      ij_out[2 * count] = I;
+      ij_out[2 * count + 1] = j;
+      // largest column the FIRST row of the tile may update inside column block j (-1: no mask)
+      if (col_limits_out) {
+        const long long lim = oz_col_limit(g, (long long)I * OZ_TM, j);
+        col_limits_out[count] = lim == 0x7fffffffffffffffLL ? -1 : lim;
+      }
+    }
+    ++count;
+  }
+  return count;
+}
+
+static int oz_gemm_launch(const void* a_slices, const double* sa, ck_i64 m, const void* b_slices, const double* sb, ck_i64 n,
+                          ck_i64 k, double* c, ck_i64 ldc, int lower, ck_i64 tb, ck_i64 gi0, ck_i64 gis, ck_i64 gj0, ck_i64 gjs,
+                          int max_ctas, void* stream) {
+  CK_REQUIRE(m >= 0 && n >= 0 && k >= 0, "negative size");
+  if (m == 0 || n == 0 || k == 0) return CK_OK;
+  CK_REQUIRE(a_slices && b_slices && sa && sb && c, "null pointer");
+  CK_REQUIRE(k % OZ_KC == 0 && k <= 1024, "k (%lld) must be a multiple of 32 and <= 1024", (long long)k);
+  CK_REQUIRE(ldc >= n, "ldc (%lld) < n (%lld)", (long long)ldc, (long long)n);
+  CK_REQUIRE((((uintptr_t)a_slices | (uintptr_t)b_slices) & 15) == 0, "slice buffers must be 16-byte aligned");
+  static CkPerDevice attr;
+  CK_SET_SMEM_ONCE(attr, ck_oz_gemm_kernel, OZ_SMEM);
+  OzGemmArgs g;
+  g.a = static_cast<const uint8_t*>(a_slices);
+  g.b = static_cast<const uint8_t*>(b_slices);
+  g.sa = sa; g.sb = sb; g.c = c; g.ldc = ldc;
+  g.kcn = (int)(k / OZ_KC);
+  oz_geometry(g, m, n, lower, tb, gi0, gis, gj0, gjs);
   g.vec = ((((uintptr_t)c) & 15) == 0 && (ldc & 1) == 0) ? 1 : 0;
   static int hints_cfg = -1;
   if (hints_cfg < 0) {

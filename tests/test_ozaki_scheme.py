@@ -47,3 +47,73 @@ def test_cokriging_through_the_scheme_matches_the_oracle():
     assert np.abs(var - ref_err ** 2).max() < 1e-11
     from scipy.linalg import cholesky
     assert np.abs(L - cholesky(sigma, lower=True)).max() < 1e-12
+
+
+# ------------------------------------------------------------------------------------------------ tile order (host-only ABI)
+def _tile_order(m, n, lower=0, tb=0, gi0=0, gis=1, gj0=0, gjs=1):
+    import ctypes
+    from cokrig_b200._lib import lib
+    nvirt = ctypes.c_int64()
+    count = lib.ck_oz_tile_order(m, n, lower, tb, gi0, gis, gj0, gjs, None, 0, ctypes.byref(nvirt), None)
+    assert count >= 0
+    ij = (ctypes.c_int * (2 * max(count, 1)))()
+    lim = (ctypes.c_int64 * max(count, 1))()
+    assert lib.ck_oz_tile_order(m, n, lower, tb, gi0, gis, gj0, gjs, ij, count, None, lim) == count
+    return np.array(ij[: 2 * count]).reshape(-1, 2), np.array(lim[:count]), nvirt.value
+
+
+def test_tile_order_covers_every_tile_exactly_once():
+    """csrc/ck_ozaki.cu oz_decode (the order the dynamic scheduler of the INT8 update kernel hands tiles out):
+    rectangular updates visit every 128 x 64 tile once; lower updates exactly the tiles that touch the lower triangle."""
+    for (m, n) in ((8832, 32768), (1000, 900), (128, 64), (5000, 131)):
+        ij, lim, nvirt = _tile_order(m, n)
+        ni, nj = -(-m // 128), -(-n // 64)
+        assert len(ij) == ni * nj == len({(i, j) for i, j in ij}) and nvirt >= len(ij)
+        assert ij[:, 0].max() == ni - 1 and ij[:, 1].max() == nj - 1 and (lim == -1).all()
+    for n in (38976, 16384, 3000, 1500, 128, 4223):
+        ij, lim, nvirt = _tile_order(n, n, lower=1)
+        ni, nj = -(-n // 128), -(-n // 64)
+        want = {(i, j) for i in range(ni) for j in range(nj) if 64 * j <= 128 * i + 127}
+        assert {(i, j) for i, j in ij} == want and len(ij) == len(want)
+        assert (lim == 128 * ij[:, 0]).all()        # first row of the tile: columns <= row
+        if n >= 16384:
+            assert nvirt <= 1.2 * len(want)   # few skipped virtual tiles: the static fallback stays balanced too
+
+
+def test_tile_order_block_cyclic_mask_matches_ck_mg_update():
+    """Block-cyclic mode: local tile (li, lj) = global tile (gi0 + li gis, gj0 + lj gjs); tiles with J > I are skipped,
+    J == I keeps its lower triangle (include/cokrig.h, ck_mg_update contract)."""
+    tb = 512
+    for (lrt, lct, gi0, gis, gj0, gjs) in ((5, 4, 1, 2, 0, 2), (3, 7, 2, 4, 1, 1), (4, 4, 0, 1, 0, 1), (2, 3, 7, 2, 8, 2)):
+        ij, lim, _ = _tile_order(lrt * tb, lct * tb, 0, tb, gi0, gis, gj0, gjs)
+        got = {(i, j) for i, j in ij}
+        want = set()
+        for I in range(lrt * tb // 128):
+            for j in range(lct * tb // 64):
+                li, lj = (I * 128) // tb, (j * 64) // tb
+                Ig, Jg = gi0 + li * gis, gj0 + lj * gjs
+                if Jg < Ig or (Jg == Ig and (j * 64 - lj * tb) <= (I * 128 + 127 - li * tb)):
+                    want.add((I, j))
+        assert got == want and len(ij) == len(want)
+        for (I, j), l in zip(ij, lim):
+            li, lj = (I * 128) // tb, (j * 64) // tb
+            diag = gi0 + li * gis == gj0 + lj * gjs
+            assert l == (lj * tb + (I * 128 - li * tb) if diag else -1)
+
+
+def test_tile_order_keeps_the_tiles_in_flight_inside_one_l2_window():
+    """What the dynamic scheduler relies on: ANY 148 consecutive tiles of the order (one per SM) touch at most two
+    super-rows' worth of A blocks and a dozen B blocks -- a few tens of MB of slices, L2-resident."""
+    ij, _, _ = _tile_order(38976, 38976, lower=1)
+    full = ij[ij[:, 0] < 16 * (305 // 16)]     # the last, partial super-row (one row block) is a plain row sweep
+    worst_a = worst_b = 0
+    worst_mb = 0.0
+    for s in range(0, len(ij) - 148, 37):
+        w = ij[s: s + 148]
+        worst_mb = max(worst_mb, (len(set(w[:, 0])) * 128 + len(set(w[:, 1])) * 64) * 1024 * 7 / 2 ** 20)
+    for s in range(0, len(full) - 148, 37):
+        w = full[s: s + 148]
+        worst_a = max(worst_a, len(set(w[:, 0])))
+        worst_b = max(worst_b, len(set(w[:, 1])))
+    assert worst_a <= 32 and worst_b <= 48, (worst_a, worst_b)
+    assert worst_mb < 80, worst_mb
