@@ -28,6 +28,23 @@ def _nvcc() -> str:
     return "nvcc"
 
 
+def _nccl_include() -> list:
+    """ck_mgctx.cu needs <nccl.h> for types and prototypes only (the library is bound at run time with dlopen): the system
+    header if there is one, else the one that ships with torch's NCCL wheel."""
+    if os.path.exists("/usr/include/nccl.h"):
+        return []
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for root in (spec.submodule_search_locations if spec else []):
+            inc = os.path.join(root, "include")
+            if os.path.exists(os.path.join(inc, "nccl.h")):
+                return ["-I", inc]
+    except Exception:  # noqa: BLE001
+        pass
+    return []
+
+
 def _deps_mtime() -> float:
     files = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
     files.append(os.path.join(HERE, "..", "include", "cokrig.h"))
@@ -47,7 +64,7 @@ def build(force: bool = False, verbose: bool = False, variant: str = "", defines
 
     def compile_one(src):
         obj = os.path.join(OBJ, src.replace(".cu", (f"_{variant}" if variant else "") + ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *_nccl_include(), *[f"-D{d}" for d in defines], "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log = r.stdout + r.stderr
         with open(obj + ".log", "w") as f:
