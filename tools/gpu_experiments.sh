@@ -33,7 +33,7 @@ for k in ('sm__pipe_tensor_subpipe_imma_cycles_active.avg.pct_of_peak_sustained_
 " >> $OUT/ozgemm_${tag}_ncu_full_summary.txt
   grep -i "gpu__time_duration\|dram__bytes\|hit_rate\|imma\|xbar2l1tex_read_bytes.sum G" $OUT/ozgemm_${tag}_ncu_full_summary.txt
 }
-TR() { local np=$1 port=$2; shift 2; python -m torch.distributed.run --nnodes=1 --nproc-per-node $np --master-addr 127.0.0.1 --master-port $port "$@"; }
+TR() { local secs=$1 np=$2 port=$3; shift 3; timeout $secs python -m torch.distributed.run --nnodes=1 --nproc-per-node $np --master-addr 127.0.0.1 --master-port $port "$@"; }
 case $WHAT in
 l2hints)
   for H in 0 3 1 2 0; do step l2hints_$H CK_OZ_L2_HINTS=$H; done 2>&1 | tee $OUT/l2hints_sweep.log
@@ -53,23 +53,23 @@ presplit)
   timeout 400 python -m pytest tests/test_gpu_ozaki.py tests/test_gpu_at_size.py tests/test_gpu_kernels.py -q -x 2>&1 | tail -3
   { step pre1 CK_OZ_PRESPLIT=1; step pre0 CK_OZ_PRESPLIT=0; step pre1b CK_OZ_PRESPLIT=1; step pre0b CK_OZ_PRESPLIT=0; } 2>&1 | tee $OUT/presplit_sweep.log ;;
 bench2)
-  timeout 500 TR 2 29561 bench.py --gpus 2 --steps 5 --warmup 3 > $OUT/bench_2gpu.json 2> $OUT/bench_2gpu.err; echo "bench2 exit=$?"
-  CK_OZ_DYNAMIC=0 timeout 300 TR 2 29562 bench.py --gpus 2 --steps 5 --warmup 3 --no-extras > $OUT/bench_2gpu_static.json 2> $OUT/bench_2gpu_static.err; echo "static exit=$?" ;;
+  TR 500 2 29561 bench.py --gpus 2 --steps 5 --warmup 3 > $OUT/bench_2gpu.json 2> $OUT/bench_2gpu.err; echo "bench2 exit=$?"
+  CK_OZ_DYNAMIC=0 TR 300 2 29562 bench.py --gpus 2 --steps 5 --warmup 3 --no-extras > $OUT/bench_2gpu_static.json 2> $OUT/bench_2gpu_static.err; echo "static exit=$?" ;;
 panel_min)
   for M in 40 24 16 32 40; do
-    CK_MG_PANEL_MIN=$M timeout 300 TR 2 2957$((M%10)) bench.py --gpus 2 --steps 5 --warmup 3 --no-extras > $OUT/bench_2gpu_pmin$M.json 2> $OUT/bench_2gpu_pmin$M.err
+    CK_MG_PANEL_MIN=$M TR 300 2 2957$((M%10)) bench.py --gpus 2 --steps 5 --warmup 3 --no-extras > $OUT/bench_2gpu_pmin$M.json 2> $OUT/bench_2gpu_pmin$M.err
     python -c "
 import json; d=json.load(open('$OUT/bench_2gpu_pmin$M.json')); print('panel_min=$M', round(d['value'],1), round(d['ms_per_step'],2), round(d['native_handle_api']['ms_per_step'],2))"
   done 2>&1 | tee $OUT/mg_panel_min_sweep_2gpu.log ;;
 native)
   NP=${2:-2}
   if [ "$NP" = 2 ]; then
-    timeout 300 TR 2 29541 tools/mg_check.py --points 3000 --targets 1000 --tile 512 --grid 1x2 --native --out $OUT/mg_native_2gpu_small_1x2.json > $OUT/mg_native_small_1x2.log 2>&1; echo "small 1x2 exit=$?"
-    timeout 400 TR 2 29542 tools/mg_check.py --points 20000 --targets 8833 --tile 1024 --grid 2x1 --native --steps 2 --skip-single --out $OUT/mg_native_2gpu_c3_2x1.json > $OUT/mg_native_c3_2x1.log 2>&1; echo "c3 2x1 exit=$?"
+    TR 300 2 29541 tools/mg_check.py --points 3000 --targets 1000 --tile 512 --grid 1x2 --native --out $OUT/mg_native_2gpu_small_1x2.json > $OUT/mg_native_small_1x2.log 2>&1; echo "small 1x2 exit=$?"
+    TR 400 2 29542 tools/mg_check.py --points 20000 --targets 8833 --tile 1024 --grid 2x1 --native --steps 2 --skip-single --out $OUT/mg_native_2gpu_c3_2x1.json > $OUT/mg_native_c3_2x1.log 2>&1; echo "c3 2x1 exit=$?"
   else
-    timeout 400 TR 4 29551 bench.py --gpus 4 --steps 3 --warmup 3 > $OUT/bench_4gpu.json 2> $OUT/bench_4gpu.err; echo "bench4 exit=$?"
+    TR 400 4 29551 bench.py --gpus 4 --steps 3 --warmup 3 > $OUT/bench_4gpu.json 2> $OUT/bench_4gpu.err; echo "bench4 exit=$?"
     for G in 4x1 1x4; do
-      timeout 200 TR 4 29552 tools/mg_check.py --points 4000 --targets 1500 --tile 512 --grid $G --native --skip-single --out $OUT/mg_native_4gpu_small_$G.json > $OUT/mg_native_4gpu_small_$G.log 2>&1; echo "small $G exit=$?"
+      TR 200 4 29552 tools/mg_check.py --points 4000 --targets 1500 --tile 512 --grid $G --native --skip-single --out $OUT/mg_native_4gpu_small_$G.json > $OUT/mg_native_4gpu_small_$G.log 2>&1; echo "small $G exit=$?"
     done
   fi ;;
 *) sed -n 2,15p "$0" ;;
