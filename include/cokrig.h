@@ -311,6 +311,8 @@ int ck_mg_unique_id(void* id128 /*HOST*/);
  * context's device.  nccl_unique_id128 may be NULL when world == 1.  Env knobs read here:
  * CK_MG_LOOKAHEAD (default 1), CK_MG_PANEL_SMS (default: adaptive per tile column), CK_MG_INT8_MIN_TILES. */
 int ck_mg_create(ck_mg_ctx** out /*HOST*/, int world, int rank, int P, int Q, ck_i64 tile, const void* nccl_unique_id128 /*HOST*/);
+/* Destroys the communicators and the panel stream.  The caller synchronises the device (or at least the streams it passed
+ * to the ck_mg_* calls) first; a context is used by one host thread at a time. */
 int ck_mg_destroy(ck_mg_ctx* h);
 int ck_mg_grid(const ck_mg_ctx* h, int* pq4 /*HOST: P, Q, p, q*/);
 
